@@ -1,0 +1,112 @@
+/* zkp_b200.h -- C ABI of the B200-native polynomial-commitment engine.
+ *
+ * The reference (sota-zk-labs/zkp-implementation) is pure Rust on arkworks and has no FFI; the
+ * drop-in seam is created at two existing function boundaries and every entry
+ * point below names the reference code it replaces.  INTEGRATION.md shows the Rust `extern "C"`
+ * block and the shim a maintainer adds to the `kzg` / `plonk` crates.
+ *
+ * Conventions
+ *   - Field elements cross the boundary exactly as arkworks stores them: little-endian u64 limbs
+ *     of the MONTGOMERY representation (Fr: 4 limbs, R = 2^256; Fq: 6 limbs, R = 2^384), so the
+ *     shim passes `fr.0.0` / `pt.x.0.0` without conversion.
+ *   - A G1 affine point is x || y (12 u64).  The point at infinity is the all-zero encoding
+ *     (0, 0) -- not on the curve -- optionally accompanied by an `infinity` byte array mirroring
+ *     ark-ec's `Affine { x, y, infinity: bool }`.
+ *   - Every function returns 0 on success or a ZKP_ERR_* code; nothing throws or aborts.  The Rust
+ *     shim maps non-zero to `panic!`, which is the reference's own error convention
+ *     (kzg/src/scheme.rs:86 `assert!`, :112 `expect`).
+ *   - Pointers are HOST memory unless the name ends in `_dev`.  The caller owns its buffers for the
+ *     duration of the call; outputs are written only on success.
+ *   - A context is bound to one GPU and one CUDA stream; calls on one context are serialised
+ *     (KzgScheme is Send + Sync in the reference).  Use one context per GPU / per process.
+ *   - There is NO CPU fallback: without a usable sm_100 device `zkp_ctx_create` fails.
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkp_ctx zkp_ctx;
+
+enum {
+  ZKP_B200_OK = 0,
+  ZKP_B200_ERR_INVALID_ARG = 1,
+  ZKP_B200_ERR_CUDA = 2,
+  ZKP_B200_ERR_OOM = 3,
+  ZKP_B200_ERR_SRS_TOO_SMALL = 4,    /* kzg/src/scheme.rs:86  assert!(g1_points.len() > polynomial.degree()) */
+  ZKP_B200_ERR_DOMAIN_TOO_LARGE = 5, /* ark-poly GeneralEvaluationDomain::new(..) == None (plonk/src/prover.rs:70) */
+  ZKP_B200_ERR_NO_DEVICE = 6,
+  ZKP_B200_ERR_EMPTY_POLY = 7        /* kzg/src/scheme.rs:112 expect("at least 1") */
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Created once next to `KzgScheme::new(srs)` (kzg/src/scheme.rs:34). */
+int zkp_ctx_create(zkp_ctx** out, int device);
+void zkp_ctx_destroy(zkp_ctx* ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
+int zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
+/* Pippenger window width in bits (0 = pick from n). */
+int zkp_ctx_set_msm_window(zkp_ctx* ctx, uint32_t bits);
+/* Kernel launches issued by the last call of the given kind (0 = MSM, 1 = NTT). */
+int zkp_ctx_last_launches(zkp_ctx* ctx, int kind);
+const char* zkp_strerror(int status);
+
+/* ---- SRS: replaces the per-call `self.0.g1_points()` clone (kzg/src/srs.rs:78-80 at
+ *      kzg/src/scheme.rs:85) with bases uploaded once and kept resident in HBM. ---------------- */
+int zkp_srs_upload(zkp_ctx* ctx, const uint64_t* xy /* n x 12 */, const uint8_t* infinity /* n or NULL */, size_t n);
+/* Adopt `n` affine points already in device memory (copied device-to-device). */
+int zkp_srs_upload_dev(zkp_ctx* ctx, const void* xy_dev, size_t n);
+size_t zkp_srs_len(const zkp_ctx* ctx);
+/* `Srs::new_from_secret` (kzg/src/srs.rs:48-69): fill the resident SRS with [secret^i * G], i < n,
+ * computed on the GPU; optionally copy the points back to `xy_out` (n x 12 u64, may be NULL). */
+int zkp_srs_generate(zkp_ctx* ctx, const uint64_t secret[4], size_t n, uint64_t* xy_out);
+
+/* ---- MSM: replaces `KzgScheme::evaluate_in_s` (kzg/src/scheme.rs:84-96) ---------------------
+ * out = sum_{i<n} scalars[i] * srs[i], normalised affine; n == 0 -> infinity (scheme.rs:94).
+ * n > zkp_srs_len -> ZKP_B200_ERR_SRS_TOO_SMALL. */
+int zkp_msm_g1(zkp_ctx* ctx, const uint64_t* scalars /* n x 4 */, size_t n, uint64_t out_xy[12], uint8_t* out_infinity);
+/* Same with ad-hoc bases (benchmark config 2: random points, not an SRS). */
+int zkp_msm_g1_bases(zkp_ctx* ctx, const uint64_t* scalars, const uint64_t* xy, const uint8_t* infinity, size_t n,
+                     uint64_t out_xy[12], uint8_t* out_infinity);
+/* Device-resident operands: scalars (n x 32 B) and, if non-NULL, bases (n x 96 B) already in HBM;
+ * bases_dev == NULL uses the resident SRS. */
+int zkp_msm_g1_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xy[12],
+                   uint8_t* out_infinity);
+/* Multi-GPU point-range sharding: each rank computes the un-normalised partial sum of its shard
+ * (XYZZ coordinates, 4 x 6 u64) ...                                                              */
+int zkp_msm_g1_partial_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xyzz[24]);
+/* ... the partials are exchanged (NCCL all-gather of 192-byte records) and folded on the host. */
+int zkp_g1_fold_partials(const uint64_t* partials_xyzz /* count x 24 */, size_t count, uint64_t out_xy[12],
+                         uint8_t* out_infinity);
+
+/* ---- NTT: replaces ark-poly `EvaluationDomain::<Fr>::{fft_in_place, ifft_in_place}` and their
+ *      coset forms, reached via `Evaluations::interpolate()` (plonk/src/prover.rs:374-375,463;
+ *      plonk/src/circuit.rs:175,230-232) and `&DensePolynomial * &DensePolynomial`
+ *      (plonk/src/prover.rs:396-437,516-548).  Natural order in and out; `inverse` includes N^-1;
+ *      coset_offset (4 u64, Montgomery) may be NULL for the plain domain. -------------------- */
+int zkp_ntt_fr(zkp_ctx* ctx, uint64_t* data /* batch x 2^log_n x 4, in place */, uint32_t log_n, size_t batch, int inverse,
+               const uint64_t* coset_offset);
+int zkp_ntt_fr_dev(zkp_ctx* ctx, void* data_dev, uint32_t log_n, size_t batch, int inverse, const uint64_t* coset_offset);
+/* `&a * &b` for DensePolynomial (2 NTT + pointwise + iNTT on the device, no host round trip).
+ * out must hold la + lb - 1 coefficients; la == 0 or lb == 0 writes nothing (zero polynomial). */
+int zkp_poly_mul_fr(zkp_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out);
+/* a[i] *= b[i] on device vectors (the pointwise step of a product kept resident). */
+int zkp_fr_mul_pointwise_dev(zkp_ctx* ctx, void* a_dev, const void* b_dev, size_t n);
+
+/* ---- synthetic workloads (bench configs 2/5): n distinct pseudo-random G1 points generated on
+ *      the device from a seed (a0 + i*delta) * G, affine, written to bases_dev (n x 96 B). ----- */
+int zkp_g1_generate_bases_dev(zkp_ctx* ctx, uint64_t seed, size_t n, void* bases_dev);
+
+/* ---- integer-pipe microbenchmark: the MSM roofline denominator.
+ *      Runs independent 32x32->64 multiply-add chains on every SM and returns multiply-adds/s. */
+int zkp_bench_imad_peak(zkp_ctx* ctx, double* wide_madds_per_s, double* lo_madds_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */

@@ -1,0 +1,229 @@
+"""zkp-implementation_b200 -- B200-native G1 MSM + Fr NTT engine behind the reference's kzg/plonk seam.
+
+This package is a thin ctypes binding over the C ABI in ``include/zkp_b200.h`` (implemented by
+``csrc/*.cu`` -> ``libzkp_b200.so``).  It is plumbing for tests, ``bench.py`` and
+``torch.distributed`` runs; the product is the shared library.
+
+There is NO CPU fallback: importing works anywhere (so the CPU test-suite can check symbols and
+host logic), but creating an :class:`Engine` without the CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import fields
+from .fields import FR_MODULUS, FQ_MODULUS
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libzkp_b200.so"
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+# name -> (restype, argtypes); every symbol include/zkp_b200.h declares
+ABI = {
+    "zkp_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "zkp_ctx_destroy": (None, [ctypes.c_void_p]),
+    "zkp_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_ctx_set_msm_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
+    "zkp_ctx_last_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "zkp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "zkp_srs_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_srs_upload_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_srs_len": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "zkp_srs_generate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "zkp_msm_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_msm_g1_bases": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_msm_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_msm_g1_partial_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.c_void_p]),
+    "zkp_g1_fold_partials": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_ntt_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_int,
+                                  ctypes.c_void_p]),
+    "zkp_ntt_fr_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_int,
+                                      ctypes.c_void_p]),
+    "zkp_poly_mul_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_void_p]),
+    "zkp_fr_mul_pointwise_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_g1_generate_bases_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p]),
+    "zkp_bench_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(ctypes.c_double)]),
+}
+
+
+class ZkpError(RuntimeError):
+    """Non-zero status from the C ABI (the Rust shim maps these to panic!, as the reference does)."""
+
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"zkp_b200 status {status}: {msg}")
+        self.status = status
+
+
+def library_path() -> str:
+    return os.path.join(PKG_DIR, LIB_NAME)
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load the C-ABI library and bind every declared symbol.  Fails loudly when it is missing."""
+    path = path or library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python zkp-implementation_b200/build.py cuda` "
+            "(nvcc, sm_100a).  This engine has no CPU fallback."
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a) -> ctypes.c_void_p:
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor (device or host)
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(int(a))
+
+
+class Engine:
+    """One context = one GPU + one CUDA stream (``zkp_ctx``)."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None, stream: Optional[int] = None):
+        self.lib = load_library(lib_path)
+        h = ctypes.c_void_p()
+        st = self.lib.zkp_ctx_create(ctypes.byref(h), int(device))
+        self._h = h if st == 0 else None
+        self._check(st)
+        self.device = device
+        if stream is not None:
+            self._check(self.lib.zkp_ctx_set_stream(self._h, ctypes.c_void_p(stream)))
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, st: int) -> None:
+        if st != 0:
+            raise ZkpError(st, self.lib.zkp_strerror(st).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.zkp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self.lib.zkp_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def set_msm_window(self, bits: int) -> None:
+        self._check(self.lib.zkp_ctx_set_msm_window(self._h, bits))
+
+    def last_launches(self, kind: str) -> int:
+        return int(self.lib.zkp_ctx_last_launches(self._h, 0 if kind == "msm" else 1))
+
+    # -- SRS --------------------------------------------------------------------------------------
+    def srs_upload(self, xy: np.ndarray, infinity: Optional[np.ndarray] = None) -> None:
+        xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 12)
+        inf = None if infinity is None else np.ascontiguousarray(infinity, dtype=np.uint8)
+        self._check(self.lib.zkp_srs_upload(self._h, _ptr(xy), _ptr(inf), xy.shape[0]))
+
+    def srs_upload_dev(self, bases_dev, n: int) -> None:
+        self._check(self.lib.zkp_srs_upload_dev(self._h, _ptr(bases_dev), n))
+
+    def srs_len(self) -> int:
+        return int(self.lib.zkp_srs_len(self._h))
+
+    def srs_generate(self, secret: int, n: int, want_points: bool = True) -> Optional[np.ndarray]:
+        sec = fields.fr_to_mont_array([secret])
+        out = np.zeros((n, 12), dtype=np.uint64) if want_points else None
+        self._check(self.lib.zkp_srs_generate(self._h, _ptr(sec), n, _ptr(out)))
+        return out
+
+    # -- MSM --------------------------------------------------------------------------------------
+    def msm(self, scalars: np.ndarray, bases: Optional[np.ndarray] = None,
+            infinity: Optional[np.ndarray] = None) -> Tuple[np.ndarray, bool]:
+        """Host buffers in, normalised affine point out (x || y Montgomery limbs, infinity flag)."""
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        inf = ctypes.c_uint8(0)
+        if bases is None:
+            st = self.lib.zkp_msm_g1(self._h, _ptr(scalars), scalars.shape[0], _ptr(out), ctypes.byref(inf))
+        else:
+            bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 12)
+            assert bases.shape[0] == scalars.shape[0]
+            finf = None if infinity is None else np.ascontiguousarray(infinity, dtype=np.uint8)
+            st = self.lib.zkp_msm_g1_bases(self._h, _ptr(scalars), _ptr(bases), _ptr(finf), scalars.shape[0], _ptr(out),
+                                           ctypes.byref(inf))
+        self._check(st)
+        return out, bool(inf.value)
+
+    def msm_dev(self, scalars_dev, bases_dev, n: int) -> Tuple[np.ndarray, bool]:
+        out = np.zeros(12, dtype=np.uint64)
+        inf = ctypes.c_uint8(0)
+        self._check(self.lib.zkp_msm_g1_dev(self._h, _ptr(scalars_dev), _ptr(bases_dev), n, _ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
+    def msm_partial_dev(self, scalars_dev, bases_dev, n: int) -> np.ndarray:
+        out = np.zeros(24, dtype=np.uint64)
+        self._check(self.lib.zkp_msm_g1_partial_dev(self._h, _ptr(scalars_dev), _ptr(bases_dev), n, _ptr(out)))
+        return out
+
+    def fold_partials(self, partials: np.ndarray) -> Tuple[np.ndarray, bool]:
+        partials = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 24)
+        out = np.zeros(12, dtype=np.uint64)
+        inf = ctypes.c_uint8(0)
+        self._check(self.lib.zkp_g1_fold_partials(_ptr(partials), partials.shape[0], _ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
+    # -- NTT --------------------------------------------------------------------------------------
+    def ntt(self, data: np.ndarray, log_n: int, batch: int = 1, inverse: bool = False,
+            coset: Optional[int] = None) -> np.ndarray:
+        """In-place on a host array of batch * 2^log_n Montgomery Fr elements (uint64 x 4 each)."""
+        assert data.dtype == np.uint64 and data.flags.c_contiguous and data.size == (batch << log_n) * 4
+        cs = None if coset is None else fields.fr_to_mont_array([coset])
+        self._check(self.lib.zkp_ntt_fr(self._h, _ptr(data), log_n, batch, 1 if inverse else 0, _ptr(cs)))
+        return data
+
+    def ntt_dev(self, data_dev, log_n: int, batch: int = 1, inverse: bool = False, coset: Optional[int] = None) -> None:
+        cs = None if coset is None else fields.fr_to_mont_array([coset])
+        self._check(self.lib.zkp_ntt_fr_dev(self._h, _ptr(data_dev), log_n, batch, 1 if inverse else 0, _ptr(cs)))
+
+    def poly_mul(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        la, lb = a.shape[0], b.shape[0]
+        if la == 0 or lb == 0:
+            return np.zeros((0, 4), dtype=np.uint64)
+        out = np.zeros((la + lb - 1, 4), dtype=np.uint64)
+        self._check(self.lib.zkp_poly_mul_fr(self._h, _ptr(a), la, _ptr(b), lb, _ptr(out)))
+        return out
+
+    def mul_pointwise_dev(self, a_dev, b_dev, n: int) -> None:
+        self._check(self.lib.zkp_fr_mul_pointwise_dev(self._h, _ptr(a_dev), _ptr(b_dev), n))
+
+    # -- synthetic workloads / microbenchmarks ----------------------------------------------------
+    def generate_bases_dev(self, seed: int, n: int, bases_dev) -> None:
+        self._check(self.lib.zkp_g1_generate_bases_dev(self._h, seed & (2**64 - 1), n, _ptr(bases_dev)))
+
+    def imad_peak(self) -> Tuple[float, float]:
+        w, l = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self.lib.zkp_bench_imad_peak(self._h, ctypes.byref(w), ctypes.byref(l)))
+        return w.value, l.value
+
+
+from .kzg import KzgCommitment, KzgOpening, KzgScheme, Srs  # noqa: E402
+
+__all__ = ["Engine", "ZkpError", "load_library", "library_path", "ABI", "fields", "Srs", "KzgScheme",
+           "KzgCommitment", "KzgOpening", "FR_MODULUS", "FQ_MODULUS"]

@@ -1,0 +1,313 @@
+// extern "C" boundary (include/zkp_b200.h): context management, host-buffer staging, result
+// normalisation.  No torch types, plain pointers and sizes.
+#include <string.h>
+
+#include <new>
+
+#include "../../include/zkp_b200.h"
+#include "engine.h"
+
+using namespace zkp;
+
+struct zkp_ctx {
+  Ctx c;
+};
+
+namespace zkp {
+int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out);
+int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t n, G1Affine* out);
+int bench_imad(Ctx* ctx, double* wide, double* lo);
+}  // namespace zkp
+
+static void write_affine(const G1Xyzz& p, uint64_t out_xy[12], uint8_t* out_inf) {
+  G1Affine a = xyzz_to_affine(p);
+  memcpy(out_xy, &a, sizeof(a));
+  if (out_inf) *out_inf = a.is_inf() ? 1 : 0;
+}
+
+extern "C" {
+
+const char* zkp_strerror(int status) {
+  switch (status) {
+    case ZKP_OK: return "ok";
+    case ZKP_ERR_INVALID_ARG: return "invalid argument";
+    case ZKP_ERR_CUDA: return "CUDA runtime error";
+    case ZKP_ERR_OOM: return "out of device memory";
+    case ZKP_ERR_SRS_TOO_SMALL: return "SRS shorter than the polynomial (g1_points.len() > polynomial.degree() violated)";
+    case ZKP_ERR_DOMAIN_TOO_LARGE: return "evaluation domain too large";
+    case ZKP_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
+    case ZKP_ERR_EMPTY_POLY: return "empty polynomial (at least 1 coefficient expected)";
+    default: return "unknown status";
+  }
+}
+
+int zkp_ctx_create(zkp_ctx** out, int device) {
+  if (!out) return ZKP_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (device < 0 || device >= rt::device_count()) return ZKP_ERR_NO_DEVICE;
+  ZKP_TRY(rt::set_device(device));
+  zkp_ctx* h = new (std::nothrow) zkp_ctx();
+  if (!h) return ZKP_ERR_OOM;
+  h->c.device = device;
+  h->c.sm_count = rt::sm_count(device);
+  if (h->c.sm_count <= 0) h->c.sm_count = 148;
+#ifndef ZKP_EMU
+  if (cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return ZKP_ERR_CUDA;
+  }
+  h->c.own_stream = true;
+#endif
+  int st = ntt_init(&h->c);
+  if (st != ZKP_OK) {
+    zkp_ctx_destroy(h);
+    return st;
+  }
+  *out = h;
+  return ZKP_OK;
+}
+
+void zkp_ctx_destroy(zkp_ctx* h) {
+  if (!h) return;
+  rt::set_device(h->c.device);
+  rt::sync(h->c.stream);
+  ntt_destroy(&h->c);
+  msm_destroy(&h->c);
+  rt::dev_free(h->c.srs);
+#ifndef ZKP_EMU
+  if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
+#endif
+  delete h;
+}
+
+int zkp_ctx_set_stream(zkp_ctx* h, void* stream) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+#ifndef ZKP_EMU
+  rt::sync(h->c.stream);
+  if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
+  h->c.stream = (cudaStream_t)stream;
+  h->c.own_stream = false;
+#else
+  (void)stream;
+#endif
+  return ZKP_OK;
+}
+
+int zkp_ctx_set_msm_window(zkp_ctx* h, uint32_t bits) {
+  if (!h || (bits != 0 && (bits < 2 || bits > 22))) return ZKP_ERR_INVALID_ARG;
+  h->c.msm_window_bits = bits;
+  return ZKP_OK;
+}
+
+int zkp_ctx_last_launches(zkp_ctx* h, int kind) {
+  if (!h) return 0;
+  return kind == 0 ? (int)h->c.msm_launches : (int)h->c.ntt_launches;
+}
+
+// ---- SRS ----------------------------------------------------------------------------------------
+static int stage_affine(Ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n, G1Affine* dev) {
+  if (!inf) return rt::h2d(dev, xy, n * sizeof(G1Affine), c->stream);
+  // honour ark-ec's `infinity: bool`: flagged entries become the (0, 0) sentinel
+  std::vector<G1Affine> tmp(n);
+  memcpy(tmp.data(), xy, n * sizeof(G1Affine));
+  for (size_t i = 0; i < n; i++)
+    if (inf[i]) tmp[i] = G1Affine::infinity();
+  ZKP_TRY(rt::h2d(dev, tmp.data(), n * sizeof(G1Affine), c->stream));
+  return rt::sync(c->stream);
+}
+
+static int srs_alloc(Ctx* c, size_t n) {
+  rt::dev_free(c->srs);
+  c->srs = nullptr;
+  c->srs_len = 0;
+  ZKP_TRY(rt::dev_malloc((void**)&c->srs, n * sizeof(G1Affine)));
+  c->srs_len = n;
+  return ZKP_OK;
+}
+
+int zkp_srs_upload(zkp_ctx* h, const uint64_t* xy, const uint8_t* infinity, size_t n) {
+  if (!h || (n && !xy)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  ZKP_TRY(srs_alloc(&h->c, n));
+  ZKP_TRY(stage_affine(&h->c, xy, infinity, n, h->c.srs));
+  return rt::sync(h->c.stream);
+}
+
+int zkp_srs_upload_dev(zkp_ctx* h, const void* xy_dev, size_t n) {
+  if (!h || (n && !xy_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  ZKP_TRY(srs_alloc(&h->c, n));
+  ZKP_TRY(rt::d2d(h->c.srs, xy_dev, n * sizeof(G1Affine), h->c.stream));
+  return rt::sync(h->c.stream);
+}
+
+size_t zkp_srs_len(const zkp_ctx* h) { return h ? h->c.srs_len : 0; }
+
+int zkp_srs_generate(zkp_ctx* h, const uint64_t secret[4], size_t n, uint64_t* xy_out) {
+  if (!h || !secret) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  ZKP_TRY(srs_alloc(&h->c, n));
+  Fr s;
+  memcpy(s.v, secret, 32);
+  ZKP_TRY(gen_srs_dev(&h->c, s, n, h->c.srs));
+  if (xy_out) ZKP_TRY(rt::d2h(xy_out, h->c.srs, n * sizeof(G1Affine), h->c.stream));
+  return rt::sync(h->c.stream);
+}
+
+// ---- MSM ----------------------------------------------------------------------------------------
+static int msm_nolock(Ctx* c, const void* scalars_dev, const void* bases_dev, size_t n, G1Xyzz* acc) {
+  const G1Affine* bases = (const G1Affine*)bases_dev;
+  if (!bases) {
+    if (n > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
+    bases = c->srs;
+  }
+  return msm_run_dev(c, (const Fr*)scalars_dev, bases, n, acc);
+}
+
+int zkp_msm_g1_partial_dev(zkp_ctx* h, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xyzz[24]) {
+  if (!h || !out_xyzz || (n && !scalars_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  G1Xyzz acc;
+  ZKP_TRY(msm_nolock(&h->c, scalars_dev, bases_dev, n, &acc));
+  memcpy(out_xyzz, &acc, sizeof(acc));
+  return ZKP_OK;
+}
+
+int zkp_msm_g1_dev(zkp_ctx* h, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xy[12],
+                   uint8_t* out_infinity) {
+  if (!h || !out_xy || (n && !scalars_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  G1Xyzz acc;
+  ZKP_TRY(msm_nolock(&h->c, scalars_dev, bases_dev, n, &acc));
+  write_affine(acc, out_xy, out_infinity);
+  return ZKP_OK;
+}
+
+int zkp_g1_fold_partials(const uint64_t* partials, size_t count, uint64_t out_xy[12], uint8_t* out_infinity) {
+  if (!out_xy || (count && !partials)) return ZKP_ERR_INVALID_ARG;
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (size_t i = 0; i < count; i++) {
+    G1Xyzz p;
+    memcpy(&p, partials + 24 * i, sizeof(p));
+    xyzz_add(acc, p);
+  }
+  write_affine(acc, out_xy, out_infinity);
+  return ZKP_OK;
+}
+
+int zkp_msm_g1(zkp_ctx* h, const uint64_t* scalars, size_t n, uint64_t out_xy[12], uint8_t* out_infinity) {
+  if (!h || !out_xy || (n && !scalars)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  Ctx* c = &h->c;
+  if (n > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
+  ZKP_TRY(rt::set_device(c->device));
+  ZKP_TRY(c->msm.scalars.reserve(n * sizeof(Fr)));
+  ZKP_TRY(rt::h2d(c->msm.scalars.p, scalars, n * sizeof(Fr), c->stream));
+  G1Xyzz acc;
+  ZKP_TRY(msm_nolock(c, c->msm.scalars.p, nullptr, n, &acc));
+  write_affine(acc, out_xy, out_infinity);
+  return ZKP_OK;
+}
+
+int zkp_msm_g1_bases(zkp_ctx* h, const uint64_t* scalars, const uint64_t* xy, const uint8_t* infinity, size_t n,
+                     uint64_t out_xy[12], uint8_t* out_infinity) {
+  if (!h || !out_xy || (n && (!scalars || !xy))) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  Ctx* c = &h->c;
+  ZKP_TRY(rt::set_device(c->device));
+  G1Xyzz acc = G1Xyzz::infinity();
+  if (n) {
+    ZKP_TRY(c->msm.scalars.reserve(n * sizeof(Fr)));
+    ZKP_TRY(c->msm.bases.reserve(n * sizeof(G1Affine)));
+    ZKP_TRY(rt::h2d(c->msm.scalars.p, scalars, n * sizeof(Fr), c->stream));
+    ZKP_TRY(stage_affine(c, xy, infinity, n, c->msm.bases.as<G1Affine>()));
+    ZKP_TRY(msm_nolock(c, c->msm.scalars.p, c->msm.bases.p, n, &acc));
+  }
+  write_affine(acc, out_xy, out_infinity);
+  return ZKP_OK;
+}
+
+// ---- NTT ----------------------------------------------------------------------------------------
+static int ntt_nolock(Ctx* c, void* data_dev, uint32_t log_n, size_t batch, int inverse, const uint64_t* coset) {
+  Fr hh;
+  if (coset) memcpy(hh.v, coset, 32);
+  return ntt_run_dev(c, (Fr*)data_dev, log_n, batch, inverse != 0, coset ? &hh : nullptr);
+}
+
+int zkp_ntt_fr_dev(zkp_ctx* h, void* data_dev, uint32_t log_n, size_t batch, int inverse, const uint64_t* coset) {
+  if (!h || (batch && !data_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return ntt_nolock(&h->c, data_dev, log_n, batch, inverse, coset);
+}
+
+int zkp_ntt_fr(zkp_ctx* h, uint64_t* data, uint32_t log_n, size_t batch, int inverse, const uint64_t* coset) {
+  if (!h || (batch && !data)) return ZKP_ERR_INVALID_ARG;
+  if (log_n > 27) return ZKP_ERR_DOMAIN_TOO_LARGE;
+  const size_t bytes = ((size_t)batch << log_n) * sizeof(Fr);
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  ZKP_TRY(h->c.ntt_io.reserve(bytes));
+  void* dev = h->c.ntt_io.p;
+  ZKP_TRY(rt::h2d(dev, data, bytes, h->c.stream));
+  ZKP_TRY(ntt_nolock(&h->c, dev, log_n, batch, inverse, coset));
+  ZKP_TRY(rt::d2h(data, dev, bytes, h->c.stream));
+  return rt::sync(h->c.stream);
+}
+
+int zkp_fr_mul_pointwise_dev(zkp_ctx* h, void* a_dev, const void* b_dev, size_t n) {
+  if (!h || (n && (!a_dev || !b_dev))) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return fr_pointwise_mul_dev(&h->c, (Fr*)a_dev, (const Fr*)b_dev, n);
+}
+
+int zkp_poly_mul_fr(zkp_ctx* h, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  if (la == 0 || lb == 0) return ZKP_OK;  // ark-poly: zero * anything = zero polynomial
+  if (!a || !b || !out) return ZKP_ERR_INVALID_ARG;
+  const size_t lo = la + lb - 1;
+  uint32_t log_n = 0;
+  while (((size_t)1 << log_n) < lo) log_n++;
+  if (log_n > 27) return ZKP_ERR_DOMAIN_TOO_LARGE;
+  const size_t N = (size_t)1 << log_n;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  Ctx* c = &h->c;
+  ZKP_TRY(rt::set_device(c->device));
+  ZKP_TRY(c->ntt_io.reserve(2 * N * sizeof(Fr)));
+  Fr* da = c->ntt_io.as<Fr>();
+  Fr* db = da + N;
+  ZKP_TRY(rt::dev_memset(da, 0, 2 * N * sizeof(Fr), c->stream));
+  ZKP_TRY(rt::h2d(da, a, la * sizeof(Fr), c->stream));
+  ZKP_TRY(rt::h2d(db, b, lb * sizeof(Fr), c->stream));
+  ZKP_TRY(ntt_run_dev(c, da, log_n, 2, false, nullptr));  // both operands as one batch of two
+  uint32_t launches = c->ntt_launches;
+  ZKP_TRY(fr_pointwise_mul_dev(c, da, db, N));
+  ZKP_TRY(ntt_run_dev(c, da, log_n, 1, true, nullptr));
+  c->ntt_launches += launches + 1;
+  ZKP_TRY(rt::d2h(out, da, lo * sizeof(Fr), c->stream));
+  return rt::sync(c->stream);
+}
+
+// ---- synthetic workloads / microbenchmarks ------------------------------------------------------
+int zkp_g1_generate_bases_dev(zkp_ctx* h, uint64_t seed, size_t n, void* bases_dev) {
+  if (!h || (n && !bases_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return gen_bases_dev(&h->c, seed, n, (G1Affine*)bases_dev);
+}
+
+int zkp_bench_imad_peak(zkp_ctx* h, double* wide, double* lo) {
+  if (!h || !wide || !lo) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return bench_imad(&h->c, wide, lo);
+}
+
+}  // extern "C"

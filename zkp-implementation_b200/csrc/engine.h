@@ -1,0 +1,99 @@
+// Engine context shared by the NTT, MSM and C-ABI translation units.
+#pragma once
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "curve.cuh"
+#include "runtime.h"
+
+namespace zkp {
+
+// Grow-only device allocation (scratch areas are sized by the largest call seen so far; 180 GB of
+// HBM per B200 makes "keep everything resident" the right default for a prover session).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return ZKP_OK;
+    rt::dev_free(p);
+    p = nullptr;
+    cap = 0;
+    ZKP_TRY(rt::dev_malloc(&p, bytes));
+    cap = bytes;
+    return ZKP_OK;
+  }
+  void release() { rt::dev_free(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Per (log_n, direction) twiddle tables, device resident.
+struct NttTables {
+  uint32_t log_n = 0;
+  bool inverse = false;
+  uint32_t npass = 0;
+  uint32_t digits[3] = {0, 0, 0};  // bits per pass, first pass = most significant input digit
+  uint32_t lb = 0;                 // boundary tables: lo has 2^lb entries, hi has 2^(log_n - lb)
+  Fr* tw_lo = nullptr;             // omega_N^i            (inverse: omega_N^-i * N^-1)
+  Fr* tw_hi = nullptr;             // omega_N^(i * 2^lb)   (inverse: omega_N^-(i * 2^lb))
+  Fr* scale = nullptr;             // N^-1 for a single-pass inverse transform, else null
+};
+
+struct CosetTables {
+  uint32_t log_n = 0;
+  bool inverse = false;
+  Fr offset;            // h (Montgomery)
+  uint32_t lb = 0;
+  Fr* lo = nullptr;     // forward: h^i ; inverse: h^-i * N^-1 is NOT folded here (N^-1 stays in tw_lo/scale)
+  Fr* hi = nullptr;     // forward: h^(i * 2^lb); inverse: h^-(i * 2^lb)
+};
+
+struct MsmScratch {
+  DevBuf scalars;       // staged host scalars
+  DevBuf bases;         // staged ad-hoc bases
+  DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
+  DevBuf bucket_start, bucket_end, task_meta, partials, seg_out, win_out;
+  DevBuf misc;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::mutex mu;        // the reference's KzgScheme is Send + Sync (plain data): calls are serialised
+
+  // SRS bases resident on the device (kzg/src/srs.rs:14-21 `g1_points`)
+  G1Affine* srs = nullptr;
+  size_t srs_len = 0;
+
+  // NTT state
+  Fr* w_fwd = nullptr;  // omega_{2^WLOG}^i, i < 2^(WLOG-1)
+  Fr* w_inv = nullptr;  // omega_{2^WLOG}^-i
+  std::map<uint32_t, NttTables> ntt_tables;  // key = log_n * 2 + inverse
+  std::vector<CosetTables> coset_tables;
+  DevBuf ntt_scratch, ntt_io, ntt_io2;
+
+  // MSM state
+  MsmScratch msm;
+  uint32_t msm_window_bits = 0;  // 0 = choose from n
+  uint32_t msm_launches = 0;     // kernels launched by the last MSM (bench.py's gpu_launches)
+  uint32_t ntt_launches = 0;
+
+  // last-call timing breakdown (CUDA-event free; filled only when profiling hooks are enabled)
+};
+
+// ---- NTT (ntt.cu) ----
+int ntt_init(Ctx* ctx);
+void ntt_destroy(Ctx* ctx);
+// In-place batched transform on device memory.  coset == nullptr -> plain domain.
+int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, const Fr* coset_host);
+int fr_pointwise_mul_dev(Ctx* ctx, Fr* a, const Fr* b, size_t n);  // a[i] *= b[i]
+
+// ---- MSM (msm.cu) ----
+// result: W window sums are reduced on the device; the final Horner over windows and the single
+// Fq inversion run on the host (272 group operations out of ~n*W).
+int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size_t n, G1Xyzz* out_host);
+void msm_destroy(Ctx* ctx);
+
+}  // namespace zkp

@@ -1,0 +1,394 @@
+// Montgomery arithmetic for BLS12-381 Fr (8 x u32) and Fq (12 x u32).
+//
+// Replaces ark-ff `Fp<MontBackend<_, 4>>` / `Fp<MontBackend<_, 6>>` as used by the reference through
+// kzg/src/types.rs:6-10 (ScalarField / BaseField).  The in-memory representation is the same as
+// arkworks': little-endian limbs of a*R mod p with R = 2^256 (Fr) or 2^384 (Fq), so a `[u64; 4]` /
+// `[u64; 6]` coming over the C ABI is reinterpreted as 8 / 12 u32 limbs with no conversion.
+//
+// Two implementations of the multiplier live here:
+//   * a portable CIOS one (64-bit temporaries) -- host code and the validation build
+//     (-DZKP_FIELD_PORTABLE) use it;
+//   * the device one: carry chains written in PTX (`mad.lo.cc/madc.hi.cc`), arranged as two
+//     interleaved accumulators (even/odd limb products) so that every lo/hi pair lands on an aligned
+//     register pair and ptxas fuses it into one IMAD.WIDE.U32 with carry-in/out.
+// The PTX primitives have a host emulation (explicit carry flag) so the very same algorithm text is
+// unit-tested on the CPU build before it ever reaches a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZKP_HD __host__ __device__ __forceinline__
+#define ZKP_HD_NOINLINE inline __host__ __device__ __noinline__
+#else
+#define ZKP_HD inline __attribute__((always_inline))
+#define ZKP_HD_NOINLINE inline __attribute__((noinline))
+#endif
+
+#if defined(__CUDA_ARCH__) && !defined(ZKP_FIELD_PORTABLE)
+#define ZKP_PTX_DEVICE 1  // device build: the even/odd carry-chain multiplier
+#else
+#define ZKP_PTX_DEVICE 0  // host pass (or validation build): portable CIOS multiplier
+#endif
+
+namespace zkp {
+
+// ------------------------------------------------------------------------------------------------
+// PTX carry-chain primitives (device) and their host emulation.
+// ------------------------------------------------------------------------------------------------
+namespace ptx {
+#if !defined(__CUDA_ARCH__)
+// Host emulation of the PTX condition-code register: one explicit carry flag per host thread.
+inline uint32_t& cf_ref() { static thread_local uint32_t cf = 0; return cf; }
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define ZKP_PTX2(name, ins, emu)                                                        \
+  ZKP_HD uint32_t name(uint32_t a, uint32_t b) {                                        \
+    uint32_t r; asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#define ZKP_PTX3(name, ins, emu)                                                        \
+  ZKP_HD uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                            \
+    uint32_t r; asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+#define ZKP_PTX2(name, ins, emu) ZKP_HD uint32_t name(uint32_t a, uint32_t b) { emu }
+#define ZKP_PTX3(name, ins, emu) ZKP_HD uint32_t name(uint32_t a, uint32_t b, uint32_t c) { emu }
+#endif
+
+ZKP_PTX2(add_cc, "add.cc.u32", uint64_t t = (uint64_t)a + b; cf_ref() = (uint32_t)(t >> 32); return (uint32_t)t;)
+ZKP_PTX2(addc_cc, "addc.cc.u32", uint64_t t = (uint64_t)a + b + cf_ref(); cf_ref() = (uint32_t)(t >> 32); return (uint32_t)t;)
+ZKP_PTX2(addc, "addc.u32", return a + b + cf_ref();)
+ZKP_PTX2(sub_cc, "sub.cc.u32", uint64_t t = (uint64_t)a - b; cf_ref() = (uint32_t)(t >> 63); return (uint32_t)t;)
+ZKP_PTX2(subc_cc, "subc.cc.u32", uint64_t t = (uint64_t)a - b - cf_ref(); cf_ref() = (uint32_t)(t >> 63); return (uint32_t)t;)
+ZKP_PTX2(subc, "subc.u32", return a - b - cf_ref();)
+ZKP_PTX2(mul_lo, "mul.lo.u32", return a * b;)
+ZKP_PTX2(mul_hi, "mul.hi.u32", return (uint32_t)(((uint64_t)a * b) >> 32);)
+ZKP_PTX3(mad_lo_cc, "mad.lo.cc.u32", uint64_t t = (uint64_t)(uint32_t)(a * b) + c; cf_ref() = (uint32_t)(t >> 32); return (uint32_t)t;)
+ZKP_PTX3(madc_lo_cc, "madc.lo.cc.u32", uint64_t t = (uint64_t)(uint32_t)(a * b) + c + cf_ref(); cf_ref() = (uint32_t)(t >> 32); return (uint32_t)t;)
+ZKP_PTX3(madc_hi_cc, "madc.hi.cc.u32", uint64_t t = (((uint64_t)a * b) >> 32) + c + cf_ref(); cf_ref() = (uint32_t)(t >> 32); return (uint32_t)t;)
+ZKP_PTX3(madc_hi, "madc.hi.u32", return (uint32_t)(((uint64_t)a * b) >> 32) + c + cf_ref();)
+#undef ZKP_PTX2
+#undef ZKP_PTX3
+}  // namespace ptx
+
+// ------------------------------------------------------------------------------------------------
+// Field parameters.  Limb tables are constexpr-function locals so that after full unrolling every
+// use folds to an immediate operand (no constant-bank or local-memory traffic).
+// ------------------------------------------------------------------------------------------------
+struct FrParams {
+  static constexpr int N = 8;
+  static constexpr uint32_t M0 = 0xffffffffu;  // -r^-1 mod 2^32
+  ZKP_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                               0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return t[i];
+  }
+  ZKP_HD static constexpr uint32_t one(int i) {  // R mod r
+    constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                               0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+    return t[i];
+  }
+  ZKP_HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+    constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                               0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    return t[i];
+  }
+};
+
+struct FqParams {
+  static constexpr int N = 12;
+  static constexpr uint32_t M0 = 0xfffcfffdu;  // -p^-1 mod 2^32
+  ZKP_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return t[i];
+  }
+  ZKP_HD static constexpr uint32_t one(int i) {  // R mod p
+    constexpr uint32_t t[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+    return t[i];
+  }
+  ZKP_HD static constexpr uint32_t r2(int i) {  // R^2 mod p
+    constexpr uint32_t t[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    return t[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fp<P>: value in Montgomery form, fully reduced ([0, p)) between operations.
+// ------------------------------------------------------------------------------------------------
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  ZKP_HD static Fp zero() { Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r; }
+  ZKP_HD static Fp one() { Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+    return r; }
+  ZKP_HD static Fp r2() { Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+    return r; }
+  ZKP_HD static Fp modulus() { Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::mod(i);
+    return r; }
+
+  ZKP_HD bool is_zero() const { uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i];
+    return o == 0; }
+  ZKP_HD bool operator==(const Fp& b) const { uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+    return o == 0; }
+  ZKP_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - p if a >= p else a        (a < 2p, no overflow out of N limbs)
+template <class P>
+ZKP_HD void fp_final_sub(Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = ptx::sub_cc(a.v[0], P::mod(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(a.v[i], P::mod(i));
+  uint32_t borrow = ptx::subc(0u, 0u);  // 0 or 0xffffffff
+#pragma unroll
+  for (int i = 0; i < N; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+  r.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);  // both moduli leave a spare top bit
+  fp_final_sub(r);
+  return r;
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = ptx::subc(0u, 0u);  // 0 or 0xffffffff
+  r.v[0] = ptx::add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], P::mod(i) & borrow);
+  r.v[N - 1] = ptx::addc(r.v[N - 1], P::mod(N - 1) & borrow);
+  return r;
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_neg(const Fp<P>& a) {
+  return fp_sub(Fp<P>::zero(), a);
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add(a, a);
+}
+
+// ---- portable CIOS Montgomery product (host path, and the -DZKP_FIELD_PORTABLE validation build) --
+template <class P>
+ZKP_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  uint32_t t[N + 1];
+#pragma unroll
+  for (int i = 0; i <= N; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      uint64_t uv = (uint64_t)a.v[j] * b.v[i] + t[j] + c;
+      t[j] = (uint32_t)uv;
+      c = uv >> 32;
+    }
+    uint64_t top = (uint64_t)t[N] + c;  // fits 33 bits; both moduli have >= 1 spare bit so top < 2^32
+    uint32_t m = t[0] * P::M0;
+    uint64_t uv = (uint64_t)m * P::mod(0) + t[0];
+    c = uv >> 32;
+#pragma unroll
+    for (int j = 1; j < N; j++) {
+      uv = (uint64_t)m * P::mod(j) + t[j] + c;
+      t[j - 1] = (uint32_t)uv;
+      c = uv >> 32;
+    }
+    uv = top + c;
+    t[N - 1] = (uint32_t)uv;
+    t[N] = (uint32_t)(uv >> 32);
+  }
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < N; i++) r.v[i] = t[i];
+  fp_final_sub(r);
+  return r;
+}
+
+// ---- even/odd carry-chain Montgomery product (device path) ---------------------------------------
+namespace detail {
+// acc[j], acc[j+1] = lo, hi of a[j]*bi for even j  (n products, n even)
+template <int n>
+ZKP_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < n; j += 2) {
+    acc[j] = ptx::mul_lo(a[j], bi);
+    acc[j + 1] = ptx::mul_hi(a[j], bi);
+  }
+}
+// acc += a[even j]*bi along one carry chain; carry-out is left in CC.CF
+template <int n>
+ZKP_HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+  acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
+  acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+  for (int j = 2; j < n; j += 2) {
+    acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+    acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+  }
+}
+// odd[j] = a[j]*bi + odd[j+2] (shift right by two limbs while accumulating); carry-in from CC.CF
+template <int n>
+ZKP_HD void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < n - 2; j += 2) {
+    odd[j] = ptx::madc_lo_cc(a[j], bi, odd[j + 2]);
+    odd[j + 1] = ptx::madc_hi_cc(a[j], bi, odd[j + 3]);
+  }
+  odd[n - 2] = ptx::madc_lo_cc(a[n - 2], bi, 0u);
+  odd[n - 1] = ptx::madc_hi(a[n - 2], bi, 0u);
+}
+
+template <class P>
+struct ModLimbs {
+  uint32_t m[P::N + 1];
+  ZKP_HD ModLimbs() {
+#pragma unroll
+    for (int i = 0; i < P::N; i++) m[i] = P::mod(i);
+    m[P::N] = 0;
+  }
+};
+
+template <class P>
+ZKP_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi, const uint32_t* mod,
+                       bool first) {
+  constexpr int n = P::N;
+  if (first) {
+    mul_n<n>(odd, a + 1, bi);
+    mul_n<n>(even, a, bi);
+  } else {
+    even[0] = ptx::add_cc(even[0], odd[1]);
+    madc_n_rshift<n>(odd, a + 1, bi);
+    cmad_n<n>(even, a, bi);
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  }
+  uint32_t mi = even[0] * P::M0;
+  cmad_n<n>(odd, mod + 1, mi);
+  cmad_n<n>(even, mod, mi);
+  odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+}
+}  // namespace detail
+
+template <class P>
+ZKP_HD Fp<P> fp_mul_chain(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int n = P::N;
+  static_assert(n % 2 == 0, "even limb count");
+  // a padded with one zero limb: the odd accumulator multiplies a[1..n] where a[n] = 0 is never read
+  // for products, but keeps the index arithmetic uniform.
+  uint32_t even[n], odd[n];
+  detail::ModLimbs<P> M;
+  uint32_t aa[n + 1];
+#pragma unroll
+  for (int i = 0; i < n; i++) aa[i] = a.v[i];
+  aa[n] = 0;
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    detail::mad_n_redc<P>(even, odd, aa, b.v[i], M.m, i == 0);
+    detail::mad_n_redc<P>(odd, even, aa, b.v[i + 1], M.m, false);
+  }
+  // merge: result limb k = even[k] + odd[k+1]
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) r.v[i] = ptx::addc_cc(even[i], odd[i + 1]);
+  r.v[n - 1] = ptx::addc(even[n - 1], 0u);
+  fp_final_sub(r);
+  return r;
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if ZKP_PTX_DEVICE || defined(ZKP_FIELD_CHAIN_ON_HOST)
+  return fp_mul_chain(a, b);
+#else
+  return fp_mul_portable(a, b);
+#endif
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul(a, a);
+}
+
+template <class P>
+ZKP_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, Fp<P>::r2()); }
+
+template <class P>
+ZKP_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> o = Fp<P>::zero();
+  o.v[0] = 1;
+  return fp_mul(a, o);
+}
+
+// a^(p-2); host-side finishing only (one call per MSM), so a plain square-and-multiply ladder.
+template <class P>
+ZKP_HD_NOINLINE Fp<P> fp_inv(const Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t e[N];
+  // p - 2 with borrow propagation (r ends in ...00000001)
+  uint32_t borrow = 2;
+  for (int i = 0; i < N; i++) {
+    uint32_t m = P::mod(i);
+    e[i] = m - borrow;
+    borrow = (m < borrow) ? 1u : 0u;
+  }
+  Fp<P> r = Fp<P>::one();
+  for (int i = N * 32 - 1; i >= 0; i--) {
+    r = fp_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, a);
+  }
+  return r;
+}
+
+template <class P>
+ZKP_HD_NOINLINE Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
+  Fp<P> r = Fp<P>::one();
+  for (int i = 63; i >= 0; i--) {
+    r = fp_sqr(r);
+    if ((e >> i) & 1) r = fp_mul(r, a);
+  }
+  return r;
+}
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+ZKP_HD Fr operator+(const Fr& a, const Fr& b) { return fp_add(a, b); }
+ZKP_HD Fr operator-(const Fr& a, const Fr& b) { return fp_sub(a, b); }
+ZKP_HD Fr operator*(const Fr& a, const Fr& b) { return fp_mul(a, b); }
+ZKP_HD Fq operator+(const Fq& a, const Fq& b) { return fp_add(a, b); }
+ZKP_HD Fq operator-(const Fq& a, const Fq& b) { return fp_sub(a, b); }
+ZKP_HD Fq operator*(const Fq& a, const Fq& b) { return fp_mul(a, b); }
+
+}  // namespace zkp

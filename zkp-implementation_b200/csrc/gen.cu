@@ -1,0 +1,220 @@
+// Setup-time generators and the integer-pipe microbenchmark.
+//
+//  * gen_srs_dev      `Srs::new_from_secret` (kzg/src/srs.rs:48-69): [secret^i * G]_{i<n}, affine.
+//                     The reference runs n serial scalar multiplications with one Fq inversion
+//                     each; here every thread owns a short run of consecutive powers and the
+//                     normalisation uses Montgomery's batch-inversion trick.
+//  * gen_bases_dev    n distinct pseudo-random points (a0 + i*delta)*G for benchmark configs 2/5
+//                     ("random points, not an SRS with known structure" -- SURVEY.md 8d).
+//  * bench_imad       independent 32x32->64 multiply-add chains on every SM: the measured
+//                     integer-pipe peak that the MSM roofline is quoted against.
+#include <string.h>
+
+#include "engine.h"
+
+namespace zkp {
+
+static constexpr uint32_t GEN_THREADS = 128;
+static constexpr uint32_t CHAIN_LEN = 64;   // points per thread in gen_bases / batch normalise
+static constexpr uint32_t SRS_RUN = 8;      // consecutive powers per thread in gen_srs
+
+__device__ __forceinline__ void gen_st_fq(Fq* p, const Fq& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+}
+
+// tmp[i] = start + i * step  (XYZZ), thread t owns [t*CHAIN_LEN, (t+1)*CHAIN_LEN)
+__global__ void __launch_bounds__(GEN_THREADS) gen_chain_kernel(G1Xyzz start, G1Affine step, size_t n, G1Xyzz* tmp) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t first = t * CHAIN_LEN;
+  if (first >= n) return;
+  G1Xyzz acc = xyzz_mul_u32(G1Xyzz::from_affine(step), (uint32_t)first);
+  xyzz_add(acc, start);
+  for (uint32_t i = 0; i < CHAIN_LEN && first + i < n; i++) {
+    tmp[first + i] = acc;
+    xyzz_madd(acc, step);
+  }
+}
+
+// tmp[i] = secret^i * G (XYZZ): MSB-first double-and-add over the canonical power, as ark-ec does
+__global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t n, G1Xyzz* tmp) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t first = t * SRS_RUN;
+  if (first >= n) return;
+  Fr cur = fp_pow_u64(secret, (uint64_t)first);
+  const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
+  for (uint32_t i = 0; i < SRS_RUN && first + i < n; i++) {
+    Fr k = fp_from_mont(cur);
+    tmp[first + i] = xyzz_mul_limbs(g, k.v, 8);
+    cur = fp_mul(cur, secret);
+  }
+}
+
+// XYZZ -> affine for runs of CHAIN_LEN points with one inversion per run (Montgomery's trick).
+// out[i].x is used as scratch for the running prefix products before it receives the result.
+__global__ void __launch_bounds__(GEN_THREADS) batch_normalise_kernel(const G1Xyzz* tmp, size_t n, G1Affine* out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t first = t * CHAIN_LEN;
+  if (first >= n) return;
+  const uint32_t cnt = (uint32_t)((n - first < CHAIN_LEN) ? (n - first) : CHAIN_LEN);
+  Fq prod = Fq::one();
+  for (uint32_t i = 0; i < cnt; i++) {
+    const G1Xyzz p = tmp[first + i];
+    gen_st_fq(&out[first + i].x, prod);
+    if (!p.is_inf()) prod = prod * (p.zz * p.zzz);
+  }
+  Fq inv = fp_inv(prod);
+  for (int i = (int)cnt - 1; i >= 0; i--) {
+    const G1Xyzz p = tmp[first + i];
+    G1Affine a = G1Affine::infinity();
+    if (!p.is_inf()) {
+      const Fq pre = out[first + i].x;
+      const Fq ti = inv * pre;          // (zz * zzz)^-1
+      inv = inv * (p.zz * p.zzz);
+      a.x = p.x * (ti * p.zzz);         // X / ZZ
+      a.y = p.y * (ti * p.zz);          // Y / ZZZ
+    }
+    gen_st_fq(&out[first + i].x, a.x);
+    gen_st_fq(&out[first + i].y, a.y);
+  }
+}
+
+static uint64_t splitmix64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+static int normalise(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) {
+  const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
+  ZKP_LAUNCH(batch_normalise_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+             ctx->stream, tmp, n, out);
+  return rt::check_last();
+}
+
+int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
+  if (n == 0) return ZKP_OK;
+  if (n >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
+  uint64_t s = seed;
+  uint32_t a0[8], dl[8];
+  for (int i = 0; i < 4; i++) {
+    uint64_t x = splitmix64(s), y = splitmix64(s);
+    a0[2 * i] = (uint32_t)x; a0[2 * i + 1] = (uint32_t)(x >> 32);
+    dl[2 * i] = (uint32_t)y; dl[2 * i + 1] = (uint32_t)(y >> 32);
+  }
+  a0[7] &= 0x3fffffffu;  // < 2^254 < r
+  dl[7] &= 0x3fffffffu;
+  dl[0] |= 1;
+  const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
+  const G1Xyzz start = xyzz_mul_limbs(g, a0, 8);
+  const G1Affine step = xyzz_to_affine(xyzz_mul_limbs(g, dl, 8));
+  DevBuf tmp;
+  ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
+  const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
+  ZKP_LAUNCH(gen_chain_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+             ctx->stream, start, step, n, tmp.as<G1Xyzz>());
+  int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
+  if (st == ZKP_OK) st = rt::sync(ctx->stream);
+  tmp.release();
+  return st;
+}
+
+int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t n, G1Affine* out) {
+  if (n == 0) return ZKP_OK;
+  DevBuf tmp;
+  ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
+  const size_t threads = (n + SRS_RUN - 1) / SRS_RUN;
+  ZKP_LAUNCH(gen_srs_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+             ctx->stream, secret, n, tmp.as<G1Xyzz>());
+  int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
+  if (st == ZKP_OK) st = rt::sync(ctx->stream);
+  tmp.release();
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-pipe peak: 16 independent multiply-add chains per thread, all SMs busy.
+// ------------------------------------------------------------------------------------------------
+#ifndef ZKP_EMU
+static constexpr int IMAD_CHAINS = 16;
+static constexpr int IMAD_INNER = 64;
+
+__global__ void __launch_bounds__(256) imad_wide_kernel(uint64_t* out, uint32_t iters, uint32_t b) {
+  uint64_t acc[IMAD_CHAINS];
+#pragma unroll
+  for (int k = 0; k < IMAD_CHAINS; k++) acc[k] = (uint64_t)(threadIdx.x + 1) * (k + 3);
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < IMAD_INNER; j++) {
+#pragma unroll
+      for (int k = 0; k < IMAD_CHAINS; k++)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[k]), "r"(b));
+    }
+  }
+  uint64_t x = 0;
+#pragma unroll
+  for (int k = 0; k < IMAD_CHAINS; k++) x ^= acc[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+__global__ void __launch_bounds__(256) imad_lo_kernel(uint64_t* out, uint32_t iters, uint32_t b) {
+  uint32_t acc[IMAD_CHAINS];
+#pragma unroll
+  for (int k = 0; k < IMAD_CHAINS; k++) acc[k] = (threadIdx.x + 1) * (k + 3);
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < IMAD_INNER; j++) {
+#pragma unroll
+      for (int k = 0; k < IMAD_CHAINS; k++)
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"((uint32_t)k));
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < IMAD_CHAINS; k++) x ^= acc[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+int bench_imad(Ctx* ctx, double* wide, double* lo) {
+  const unsigned blocks = (unsigned)ctx->sm_count * 8, threads = 256;
+  const uint32_t iters = 256;
+  DevBuf out;
+  ZKP_TRY(out.reserve((size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best[2] = {0, 0};
+  for (int which = 0; which < 2; which++) {
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, ctx->stream);
+      if (which == 0) imad_wide_kernel<<<blocks, threads, 0, ctx->stream>>>(out.as<uint64_t>(), iters, 0x9e3779b9u);
+      else imad_lo_kernel<<<blocks, threads, 0, ctx->stream>>>(out.as<uint64_t>(), iters, 0x9e3779b9u);
+      cudaEventRecord(e1, ctx->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double ops = (double)blocks * threads * iters * IMAD_INNER * IMAD_CHAINS;
+      const double rate = ops / (ms * 1e-3);
+      if (rep > 0 && rate > best[which]) best[which] = rate;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  out.release();
+  *wide = best[0];
+  *lo = best[1];
+  return rt::check_last();
+}
+#else
+int bench_imad(Ctx*, double* wide, double* lo) {
+  *wide = 0;
+  *lo = 0;
+  return ZKP_OK;
+}
+#endif
+
+}  // namespace zkp

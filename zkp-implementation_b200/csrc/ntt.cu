@@ -1,0 +1,425 @@
+// Radix-2 NTT / iNTT / coset-NTT over BLS12-381 Fr, natural order in and out.
+//
+// Replaces ark-poly 0.4 `Radix2EvaluationDomain::{fft_in_place, ifft_in_place}` (and the coset
+// variants) that the reference reaches through `Evaluations::interpolate()`
+// (plonk/src/prover.rs:374-375,463; plonk/src/circuit.rs:175,230-232) and through
+// `&DensePolynomial * &DensePolynomial` (plonk/src/prover.rs:396-437,516-548).
+// Definition reproduced: omega_N = 7^((r-1)/N),
+//   forward  X[k] = sum_j x[j] (h omega^k)^j          (h = coset offset, 1 by default)
+//   inverse  x[j] = h^-j N^-1 sum_k X[k] omega^(-jk)
+// Field arithmetic is exact, so any correct schedule is element-for-element identical.
+//
+// Schedule: N = N1 * N2 * N3 (<= 3 passes of <= 2^9 points).  Pass i runs, for every fixed value of
+// the other index digits, one N_i-point transform on a shared-memory tile that also carries 2^q
+// neighbouring columns (so every global access is a run of 2^q * 32 contiguous bytes), multiplies
+// by the inter-pass twiddle omega_{M_i}^(low * k_i) and writes the digit back in place.  The last
+// pass writes transposed, which puts the digit-reversed result in natural order without a separate
+// permutation sweep.  Pass 1 reads `data` and writes `scratch`, the last pass writes back to
+// `data`: 64 * N bytes of HBM traffic per pass, nothing else.
+#include "engine.h"
+
+namespace zkp {
+
+static constexpr uint32_t WLOG = 11;       // sub-transform twiddle table: omega_{2^11}^i, i < 2^10
+static constexpr uint32_t RMAX = 9;        // largest digit of a multi-pass schedule
+static constexpr uint32_t TILE_LOG = 11;   // elements per shared-memory tile (64 KB)
+static constexpr uint32_t SINGLE_MAX = 11; // largest transform done in one tile
+static constexpr uint32_t NTT_THREADS = 256;
+
+struct NttPassArgs {
+  const Fr* in;
+  Fr* out;
+  uint32_t log_n, r, q, s;
+  uint32_t mode;      // 0: strided in-place digit, 1: last digit (transposing write)
+  uint32_t log_n1, log_mid;
+  const Fr* w;        // sub-transform twiddles
+  const Fr* tw_lo;    // inter-pass twiddles (mode 0)
+  const Fr* tw_hi;
+  uint32_t tw_lb, tw_shift, tw_two_level;
+  const Fr* pre_lo;   // load-time scale by table[addr] (coset forward), or null
+  const Fr* pre_hi;
+  uint32_t pre_lb;
+  const Fr* post_lo;  // store-time scale by table[addr] (coset inverse), or null
+  const Fr* post_hi;
+  uint32_t post_lb;
+  const Fr* scale;    // store-time constant (N^-1 on the single-pass inverse), or null
+  size_t batch_stride;
+};
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// Shared-memory tile: two planes of 16-byte halves so that consecutive lanes touch consecutive
+// 16-byte words (conflict-free for unit-stride element access).
+__device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i) {
+  uint4 a = lo[i], b = hi[i];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_tile(uint4* lo, uint4* hi, uint32_t i, const Fr& r) {
+  lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// K decimation-in-frequency levels (l0 .. l0+K-1 of an r-level transform along the tile rows) held
+// in registers: each work item owns the 2^K rows that differ in bits [lo_bit, lo_bit + K).
+template <int K>
+__device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, uint32_t r, uint32_t q, uint32_t l0,
+                                          const Fr* __restrict__ w, uint32_t tid, uint32_t nthreads) {
+  const uint32_t lo_bit = r - l0 - K;
+  const uint32_t items = 1u << (r - K + q);
+  const uint32_t qmask = (1u << q) - 1;
+  for (uint32_t it = tid; it < items; it += nthreads) {
+    const uint32_t c = it & qmask;
+    const uint32_t jr = it >> q;
+    const uint32_t dlow = jr & ((1u << lo_bit) - 1);
+    const uint32_t base_d = ((jr >> lo_bit) << (lo_bit + K)) | dlow;
+    Fr e[1 << K];
+#pragma unroll
+    for (int m = 0; m < (1 << K); m++) e[m] = ld_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c);
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+      const int hm = 1 << (K - 1 - t);
+      const uint32_t order_log = lo_bit + K - t;  // butterflies of this level use omega_{2^order_log}
+      const uint32_t wshift = WLOG - order_log;
+#pragma unroll
+      for (int m = 0; m < (1 << K); m++) {
+        if (m & hm) continue;
+        Fr u = e[m], v = e[m + hm];
+        e[m] = fp_add(u, v);
+        Fr d = fp_sub(u, v);
+        if (order_log == 1) {
+          e[m + hm] = d;  // omega_2^0 = 1 on the last level
+        } else {
+          const uint32_t j = dlow + ((uint32_t)(m & (hm - 1)) << lo_bit);
+          e[m + hm] = fp_mul(d, ldg_fr(w + ((size_t)j << wshift)));
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < (1 << K); m++) st_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c, e[m]);
+  }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
+  ZKP_DYN_SMEM(uint4, sm);
+  const uint32_t r = a.r, q = a.q, s = a.s;
+  const uint32_t E = 1u << (r + q);
+  uint4* lo = sm;
+  uint4* hi = sm + E;
+  const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
+  const uint32_t tile = blockIdx.x;
+  const Fr* in = a.in + (size_t)blockIdx.y * a.batch_stride;
+  Fr* out = a.out + (size_t)blockIdx.y * a.batch_stride;
+  const uint32_t qmask = (1u << q) - 1, rmask = (1u << r) - 1;
+
+  // ---- tile geometry ----
+  uint32_t base = 0, cb = 0, mid = 0, ab = 0;
+  if (a.mode == 0) {
+    const uint32_t ncb_log = s - q;
+    const uint32_t outer = tile >> ncb_log;
+    cb = tile & ((1u << ncb_log) - 1);
+    base = (outer << (s + r)) + (cb << q);
+  } else {
+    const uint32_t nab_log = a.log_n1 - q;
+    mid = tile >> nab_log;
+    ab = tile & ((1u << nab_log) - 1);
+  }
+
+  // ---- load (optionally scaled by the coset powers h^addr) ----
+  for (uint32_t idx = tid; idx < E; idx += nthreads) {
+    uint32_t addr, sidx;
+    if (a.mode == 0) {
+      const uint32_t c = idx & qmask, d = idx >> q;
+      addr = base + (d << s) + c;
+      sidx = idx;
+    } else {
+      const uint32_t d = idx & rmask, c = idx >> r;
+      const uint32_t k1 = (ab << q) + c;
+      addr = (((k1 << a.log_mid) + mid) << r) + d;
+      sidx = (d << q) + c;
+    }
+    Fr v = ld_fr(in + addr);
+    if (a.pre_lo) {
+      v = fp_mul(v, ldg_fr(a.pre_lo + (addr & ((1u << a.pre_lb) - 1))));
+      v = fp_mul(v, ldg_fr(a.pre_hi + (addr >> a.pre_lb)));
+    }
+    st_tile(lo, hi, sidx, v);
+  }
+  __syncthreads();
+
+  // ---- r DIF levels on the tile rows (result row d holds output digit bitrev_r(d)) ----
+  uint32_t l0 = 0;
+  while (r - l0 >= 3) {
+    tile_step<3>(lo, hi, r, q, l0, a.w, tid, nthreads);
+    __syncthreads();
+    l0 += 3;
+  }
+  if (r - l0 == 2) {
+    tile_step<2>(lo, hi, r, q, l0, a.w, tid, nthreads);
+    __syncthreads();
+  } else if (r - l0 == 1) {
+    tile_step<1>(lo, hi, r, q, l0, a.w, tid, nthreads);
+    __syncthreads();
+  }
+
+  // ---- store: un-bit-reverse the digit, apply inter-pass twiddle / coset / N^-1 ----
+  for (uint32_t idx = tid; idx < E; idx += nthreads) {
+    const uint32_t c = idx & qmask, k = idx >> q;
+    const uint32_t d = r ? (__brev(k) >> (32 - r)) : 0;
+    Fr v = ld_tile(lo, hi, (d << q) + c);
+    uint32_t addr;
+    if (a.mode == 0) {
+      const uint32_t col = (cb << q) + c;
+      const uint64_t e = ((uint64_t)col * k) << a.tw_shift;
+      v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
+      if (a.tw_two_level) v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
+      addr = base + (k << s) + c;
+    } else {
+      const uint32_t k1 = (ab << q) + c;
+      addr = k1 + (mid << a.log_n1) + (k << (a.log_n - r));
+      if (a.post_lo) {
+        v = fp_mul(v, ldg_fr(a.post_lo + (addr & ((1u << a.post_lb) - 1))));
+        v = fp_mul(v, ldg_fr(a.post_hi + (addr >> a.post_lb)));
+      }
+      if (a.scale) v = fp_mul(v, ldg_fr(a.scale));
+    }
+    st_fr(out + addr, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) fr_pointwise_mul_kernel(Fr* a, const Fr* b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) st_fr(a + i, fp_mul(ld_fr(a + i), ld_fr(b + i)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: schedules and twiddle tables
+// ------------------------------------------------------------------------------------------------
+static Fr fr_root_of_unity_2_32() {
+  // 7^((r-1)/2^32): the exponent is r-1 shifted down one 32-bit limb (low limb of r-1 is zero)
+  Fr seven = Fr::zero();
+  seven.v[0] = 7;
+  seven = fp_to_mont(seven);
+  Fr acc = Fr::one();
+  for (int i = 7 * 32 - 1; i >= 0; i--) {
+    acc = fp_sqr(acc);
+    const uint32_t limb = FrParams::mod(1 + (i >> 5));
+    if ((limb >> (i & 31)) & 1) acc = fp_mul(acc, seven);
+  }
+  return acc;
+}
+
+static Fr fr_omega(uint32_t log_n) {  // group_gen of the size-2^log_n domain
+  Fr w = fr_root_of_unity_2_32();
+  for (uint32_t i = log_n; i < 32; i++) w = fp_sqr(w);
+  return w;
+}
+
+static Fr fr_from_u64(uint64_t x) {
+  Fr a = Fr::zero();
+  a.v[0] = (uint32_t)x;
+  a.v[1] = (uint32_t)(x >> 32);
+  return fp_to_mont(a);
+}
+
+static int upload_powers(Ctx* ctx, Fr** dev, const Fr& base, const Fr& first, size_t count) {
+  std::vector<Fr> h(count);
+  Fr cur = first;
+  for (size_t i = 0; i < count; i++) {
+    h[i] = cur;
+    cur = fp_mul(cur, base);
+  }
+  ZKP_TRY(rt::dev_malloc((void**)dev, count * sizeof(Fr)));
+  ZKP_TRY(rt::h2d(*dev, h.data(), count * sizeof(Fr), ctx->stream));
+  return rt::sync(ctx->stream);
+}
+
+int ntt_init(Ctx* ctx) {
+  Fr w = fr_omega(WLOG);
+  ZKP_TRY(upload_powers(ctx, &ctx->w_fwd, w, Fr::one(), (size_t)1 << (WLOG - 1)));
+  ZKP_TRY(upload_powers(ctx, &ctx->w_inv, fp_inv(w), Fr::one(), (size_t)1 << (WLOG - 1)));
+  return rt::allow_smem((const void*)ntt_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr));
+}
+
+void ntt_destroy(Ctx* ctx) {
+  rt::dev_free(ctx->w_fwd);
+  rt::dev_free(ctx->w_inv);
+  for (auto& kv : ctx->ntt_tables) {
+    rt::dev_free(kv.second.tw_lo);
+    rt::dev_free(kv.second.tw_hi);
+    rt::dev_free(kv.second.scale);
+  }
+  for (auto& c : ctx->coset_tables) {
+    rt::dev_free(c.lo);
+    rt::dev_free(c.hi);
+  }
+  ctx->ntt_tables.clear();
+  ctx->coset_tables.clear();
+  ctx->ntt_scratch.release();
+  ctx->ntt_io.release();
+  ctx->ntt_io2.release();
+}
+
+static int get_tables(Ctx* ctx, uint32_t log_n, bool inverse, NttTables** out) {
+  const uint32_t key = log_n * 2 + (inverse ? 1 : 0);
+  auto it = ctx->ntt_tables.find(key);
+  if (it != ctx->ntt_tables.end()) {
+    *out = &it->second;
+    return ZKP_OK;
+  }
+  NttTables t;
+  t.log_n = log_n;
+  t.inverse = inverse;
+  if (log_n <= SINGLE_MAX) {
+    t.npass = 1;
+    t.digits[0] = log_n;
+  } else {
+    t.npass = (log_n + RMAX - 1) / RMAX;
+    if (t.npass > 3) return ZKP_ERR_DOMAIN_TOO_LARGE;
+    const uint32_t b = log_n / t.npass, rem = log_n % t.npass;
+    for (uint32_t i = 0; i < t.npass; i++) t.digits[i] = b + (i < rem ? 1 : 0);
+  }
+  Fr n_inv = fp_inv(fr_from_u64((uint64_t)1 << log_n));
+  if (t.npass == 1) {
+    if (inverse) {
+      ZKP_TRY(upload_powers(ctx, &t.scale, Fr::one(), n_inv, 1));
+    }
+  } else {
+    t.lb = t.digits[0];
+    Fr w = fr_omega(log_n);
+    if (inverse) w = fp_inv(w);
+    Fr whi = w;
+    for (uint32_t i = 0; i < t.lb; i++) whi = fp_sqr(whi);
+    ZKP_TRY(upload_powers(ctx, &t.tw_lo, w, inverse ? n_inv : Fr::one(), (size_t)1 << t.lb));
+    ZKP_TRY(upload_powers(ctx, &t.tw_hi, whi, Fr::one(), (size_t)1 << (log_n - t.lb)));
+  }
+  auto ins = ctx->ntt_tables.emplace(key, t);
+  *out = &ins.first->second;
+  return ZKP_OK;
+}
+
+static int get_coset(Ctx* ctx, uint32_t log_n, bool inverse, const Fr& h, CosetTables** out) {
+  for (auto& c : ctx->coset_tables)
+    if (c.log_n == log_n && c.inverse == inverse && c.offset == h) {
+      *out = &c;
+      return ZKP_OK;
+    }
+  if (ctx->coset_tables.size() >= 8) {  // small LRU-less cache: drop the oldest entry
+    rt::dev_free(ctx->coset_tables.front().lo);
+    rt::dev_free(ctx->coset_tables.front().hi);
+    ctx->coset_tables.erase(ctx->coset_tables.begin());
+  }
+  CosetTables c;
+  c.log_n = log_n;
+  c.inverse = inverse;
+  c.offset = h;
+  c.lb = log_n / 2;
+  Fr g = inverse ? fp_inv(h) : h;
+  Fr ghi = g;
+  for (uint32_t i = 0; i < c.lb; i++) ghi = fp_sqr(ghi);
+  ZKP_TRY(upload_powers(ctx, &c.lo, g, Fr::one(), (size_t)1 << c.lb));
+  ZKP_TRY(upload_powers(ctx, &c.hi, ghi, Fr::one(), (size_t)1 << (log_n - c.lb)));
+  ctx->coset_tables.push_back(c);
+  *out = &ctx->coset_tables.back();
+  return ZKP_OK;
+}
+
+int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, const Fr* coset_host) {
+  ctx->ntt_launches = 0;
+  if (batch == 0) return ZKP_OK;
+  if (log_n > 27) return ZKP_ERR_DOMAIN_TOO_LARGE;
+  if (batch > 65535) return ZKP_ERR_INVALID_ARG;
+  if (log_n == 0) return ZKP_OK;  // size-1 domain: identity in both directions (h^0 = 1, 1^-1 = 1)
+  NttTables* t = nullptr;
+  ZKP_TRY(get_tables(ctx, log_n, inverse, &t));
+  CosetTables* cs = nullptr;
+  if (coset_host) {
+    const Fr one = Fr::one();
+    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, &cs));
+  }
+  const size_t N = (size_t)1 << log_n;
+  Fr* scratch = nullptr;
+  if (t->npass > 1) {
+    ZKP_TRY(ctx->ntt_scratch.reserve(N * batch * sizeof(Fr)));
+    scratch = ctx->ntt_scratch.as<Fr>();
+  }
+  uint32_t below = log_n;  // bits below the current digit + the digit itself
+  for (uint32_t i = 0; i < t->npass; i++) {
+    const uint32_t r = t->digits[i];
+    below -= r;
+    const bool last = (i + 1 == t->npass);
+    NttPassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = (i == 0) ? data : scratch;
+    a.out = last ? data : scratch;
+    a.log_n = log_n;
+    a.r = r;
+    a.s = below;
+    a.w = inverse ? ctx->w_inv : ctx->w_fwd;
+    a.batch_stride = N;
+    if (!last) {
+      a.mode = 0;
+      a.q = (TILE_LOG - r < a.s) ? (TILE_LOG - r) : a.s;
+      a.tw_lo = t->tw_lo;
+      a.tw_hi = t->tw_hi;
+      a.tw_lb = t->lb;
+      a.tw_shift = log_n - (a.s + r);
+      a.tw_two_level = (a.tw_shift < t->lb) ? 1 : 0;
+    } else {
+      a.mode = 1;
+      if (t->npass == 1) {
+        a.log_n1 = 0;
+        a.log_mid = 0;
+        a.q = 0;
+        a.scale = t->scale;
+      } else {
+        a.log_n1 = t->digits[0];
+        a.log_mid = (t->npass == 3) ? t->digits[1] : 0;
+        a.q = (TILE_LOG - r < a.log_n1) ? (TILE_LOG - r) : a.log_n1;
+      }
+    }
+    if (i == 0 && cs && !inverse) { a.pre_lo = cs->lo; a.pre_hi = cs->hi; a.pre_lb = cs->lb; }
+    if (last && cs && inverse) { a.post_lo = cs->lo; a.post_hi = cs->hi; a.post_lb = cs->lb; }
+    const uint32_t E = 1u << (r + a.q);
+    const uint32_t tiles = (uint32_t)(N >> (r + a.q));
+    uint32_t threads = NTT_THREADS;
+    while (threads > 32 && threads > E / 2) threads >>= 1;
+    dim3 grid(tiles, (unsigned)batch, 1);
+    ZKP_LAUNCH(ntt_pass_kernel, grid, dim3(threads), (size_t)E * sizeof(Fr), ctx->stream, a);
+    ctx->ntt_launches++;
+  }
+  return rt::check_last();
+}
+
+int fr_pointwise_mul_dev(Ctx* ctx, Fr* a, const Fr* b, size_t n) {
+  if (n == 0) return ZKP_OK;
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  ZKP_LAUNCH(fr_pointwise_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, a, b, n);
+  return rt::check_last();
+}
+
+}  // namespace zkp
