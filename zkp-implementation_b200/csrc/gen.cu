@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "engine.h"
+#include "memops.cuh"
 
 namespace zkp {
 
@@ -18,22 +19,17 @@ static constexpr uint32_t GEN_THREADS = 128;
 static constexpr uint32_t CHAIN_LEN = 64;   // points per thread in gen_bases / batch normalise
 static constexpr uint32_t SRS_RUN = 8;      // consecutive powers per thread in gen_srs
 
-__device__ __forceinline__ void gen_st_fq(Fq* p, const Fq& r) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
-  q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
-}
-
 // tmp[i] = start + i * step  (XYZZ), thread t owns [t*CHAIN_LEN, (t+1)*CHAIN_LEN)
-__global__ void __launch_bounds__(GEN_THREADS) gen_chain_kernel(G1Xyzz start, G1Affine step, size_t n, G1Xyzz* tmp) {
+__global__ void __launch_bounds__(GEN_THREADS) gen_chain_kernel(const G1Xyzz* start_p, const G1Affine* step_p, size_t n, G1Xyzz* tmp) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t first = t * CHAIN_LEN;
   if (first >= n) return;
+  const G1Affine step = ld_affine(step_p);
+  const G1Xyzz start = ld_xyzz(start_p);
   G1Xyzz acc = xyzz_mul_u32(G1Xyzz::from_affine(step), (uint32_t)first);
   xyzz_add(acc, start);
   for (uint32_t i = 0; i < CHAIN_LEN && first + i < n; i++) {
-    tmp[first + i] = acc;
+    st_xyzz(tmp + first + i, acc);
     xyzz_madd(acc, step);
   }
 }
@@ -47,7 +43,7 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t 
   const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
   for (uint32_t i = 0; i < SRS_RUN && first + i < n; i++) {
     Fr k = fp_from_mont(cur);
-    tmp[first + i] = xyzz_mul_limbs(g, k.v, 8);
+    st_xyzz(tmp + first + i, xyzz_mul_limbs(g, k.v, 8));
     cur = fp_mul(cur, secret);
   }
 }
@@ -61,23 +57,23 @@ __global__ void __launch_bounds__(GEN_THREADS) batch_normalise_kernel(const G1Xy
   const uint32_t cnt = (uint32_t)((n - first < CHAIN_LEN) ? (n - first) : CHAIN_LEN);
   Fq prod = Fq::one();
   for (uint32_t i = 0; i < cnt; i++) {
-    const G1Xyzz p = tmp[first + i];
-    gen_st_fq(&out[first + i].x, prod);
+    const G1Xyzz p = ld_xyzz(tmp + first + i);
+    st_fq(&out[first + i].x, prod);
     if (!p.is_inf()) prod = prod * (p.zz * p.zzz);
   }
   Fq inv = fp_inv(prod);
   for (int i = (int)cnt - 1; i >= 0; i--) {
-    const G1Xyzz p = tmp[first + i];
+    const G1Xyzz p = ld_xyzz(tmp + first + i);
     G1Affine a = G1Affine::infinity();
     if (!p.is_inf()) {
-      const Fq pre = out[first + i].x;
+      const Fq pre = ld_fq(&out[first + i].x);
       const Fq ti = inv * pre;          // (zz * zzz)^-1
       inv = inv * (p.zz * p.zzz);
       a.x = p.x * (ti * p.zzz);         // X / ZZ
       a.y = p.y * (ti * p.zz);          // Y / ZZZ
     }
-    gen_st_fq(&out[first + i].x, a.x);
-    gen_st_fq(&out[first + i].y, a.y);
+    st_fq(&out[first + i].x, a.x);
+    st_fq(&out[first + i].y, a.y);
   }
 }
 
@@ -113,10 +109,16 @@ int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
   const G1Xyzz start = xyzz_mul_limbs(g, a0, 8);
   const G1Affine step = xyzz_to_affine(xyzz_mul_limbs(g, dl, 8));
   DevBuf tmp;
-  ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
+  ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz) + sizeof(G1Xyzz) + sizeof(G1Affine)));
+  // chain parameters live in device memory (large by-value kernel parameters are avoided)
+  G1Xyzz* start_d = tmp.as<G1Xyzz>() + n;
+  G1Affine* step_d = reinterpret_cast<G1Affine*>(start_d + 1);
+  ZKP_TRY(rt::h2d(start_d, &start, sizeof(start), ctx->stream));
+  ZKP_TRY(rt::h2d(step_d, &step, sizeof(step), ctx->stream));
+  ZKP_TRY(rt::sync(ctx->stream));
   const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
   ZKP_LAUNCH(gen_chain_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
-             ctx->stream, start, step, n, tmp.as<G1Xyzz>());
+             ctx->stream, start_d, step_d, n, tmp.as<G1Xyzz>());
   int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
   if (st == ZKP_OK) st = rt::sync(ctx->stream);
   tmp.release();
@@ -143,21 +145,27 @@ int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t n, G1Affine* out) {
 static constexpr int IMAD_CHAINS = 16;
 static constexpr int IMAD_INNER = 64;
 
+// The multiplier the field code actually issues: mad.lo.cc / madc.hi.cc pairs on one carry chain,
+// which ptxas fuses into IMAD.WIDE.U32.X (32x32+64 with carry in/out).  The multiplicand of every
+// link comes from another chain's previous result so nothing is loop-invariant.
 __global__ void __launch_bounds__(256) imad_wide_kernel(uint64_t* out, uint32_t iters, uint32_t b) {
-  uint64_t acc[IMAD_CHAINS];
+  uint32_t lo[IMAD_CHAINS], hi[IMAD_CHAINS];
 #pragma unroll
-  for (int k = 0; k < IMAD_CHAINS; k++) acc[k] = (uint64_t)(threadIdx.x + 1) * (k + 3);
+  for (int k = 0; k < IMAD_CHAINS; k++) { lo[k] = (threadIdx.x + 1) * (k + 3); hi[k] = lo[k] ^ 0x55555555u; }
   for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
     for (int j = 0; j < IMAD_INNER; j++) {
+      asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                   : "+r"(lo[0]), "+r"(hi[0]) : "r"(hi[5]), "r"(b));
 #pragma unroll
-      for (int k = 0; k < IMAD_CHAINS; k++)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[k]), "r"(b));
+      for (int k = 1; k < IMAD_CHAINS; k++)
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(lo[k]), "+r"(hi[k]) : "r"(hi[(k + 5) % IMAD_CHAINS]), "r"(b));
     }
   }
   uint64_t x = 0;
 #pragma unroll
-  for (int k = 0; k < IMAD_CHAINS; k++) x ^= acc[k];
+  for (int k = 0; k < IMAD_CHAINS; k++) x ^= lo[k] ^ ((uint64_t)hi[k] << 32);
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(256) imad_lo_kernel(uint64_t* out, uint32_t it
     for (int j = 0; j < IMAD_INNER; j++) {
 #pragma unroll
       for (int k = 0; k < IMAD_CHAINS; k++)
-        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"((uint32_t)k));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(acc[(k + 5) % IMAD_CHAINS]), "r"(b));
     }
   }
   uint32_t x = 0;

@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "engine.h"
+#include "memops.cuh"
 
 #ifndef ZKP_EMU
 #include <cub/cub.cuh>
@@ -39,37 +40,6 @@ struct MsmTask {
   uint32_t start;  // index into the window-major sorted value array
   uint32_t len;
 };
-
-// ---- 48-byte / 192-byte vector loads -----------------------------------------------------------
-__device__ __forceinline__ Fq ld_fq(const Fq* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1], c = q[2];
-  Fq r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
-  return r;
-}
-__device__ __forceinline__ void st_fq(Fq* p, const Fq& r) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
-  q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
-}
-__device__ __forceinline__ G1Affine ld_affine(const G1Affine* p) {
-  G1Affine r;
-  r.x = ld_fq(&p->x);
-  r.y = ld_fq(&p->y);
-  return r;
-}
-__device__ __forceinline__ G1Xyzz ld_xyzz(const G1Xyzz* p) {
-  G1Xyzz r;
-  r.x = ld_fq(&p->x); r.y = ld_fq(&p->y); r.zz = ld_fq(&p->zz); r.zzz = ld_fq(&p->zzz);
-  return r;
-}
-__device__ __forceinline__ void st_xyzz(G1Xyzz* p, const G1Xyzz& r) {
-  st_fq(&p->x, r.x); st_fq(&p->y, r.y); st_fq(&p->zz, r.zz); st_fq(&p->zzz, r.zzz);
-}
 
 // ---- 1. recode ---------------------------------------------------------------------------------
 // keys[w*n + i] = |digit| - 1 (bucket index, weight |digit|) or nbuckets for a zero digit
@@ -223,17 +193,17 @@ __global__ void __launch_bounds__(RED_THREADS) msm_window_reduce_kernel(const G1
     G1Xyzz p = ld_xyzz(seg_out + (size_t)w * nseg + i);
     xyzz_add(acc, p);
   }
-  sh[tid] = acc;
+  st_xyzz(&sh[tid], acc);
   __syncthreads();
   for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
     if (tid < s) {
-      G1Xyzz a = sh[tid], b = sh[tid + s];
+      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
       xyzz_add(a, b);
-      sh[tid] = a;
+      st_xyzz(&sh[tid], a);
     }
     __syncthreads();
   }
-  if (tid == 0) st_xyzz(win_out + w, sh[0]);
+  if (tid == 0) st_xyzz(win_out + w, ld_xyzz(&sh[0]));
 }
 
 // ------------------------------------------------------------------------------------------------

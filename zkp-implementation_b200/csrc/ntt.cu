@@ -17,6 +17,7 @@
 // permutation sweep.  Pass 1 reads `data` and writes `scratch`, the last pass writes back to
 // `data`: 64 * N bytes of HBM traffic per pass, nothing else.
 #include "engine.h"
+#include "memops.cuh"
 
 namespace zkp {
 
@@ -46,27 +47,6 @@ struct NttPassArgs {
   size_t batch_stride;
 };
 
-__device__ __forceinline__ Fr ld_fr(const Fr* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
-  Fr r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  Fr r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
-}
 // Shared-memory tile: two planes of 16-byte halves so that consecutive lanes touch consecutive
 // 16-byte words (conflict-free for unit-stride element access).
 __device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i) {
