@@ -52,8 +52,14 @@ void zkp_ctx_destroy(zkp_ctx* ctx);
 int zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 /* Pippenger window width in bits (0 = pick from n). */
 int zkp_ctx_set_msm_window(zkp_ctx* ctx, uint32_t bits);
-/* Kernel launches issued by the last call of the given kind (0 = MSM, 1 = NTT). */
+/* Kernel launches issued by the last call of the given kind (0 = MSM, 1 = NTT); kind 2 / 3 return
+ * the window width c / window count W the last MSM used. */
 int zkp_ctx_last_launches(zkp_ctx* ctx, int kind);
+/* Per-phase device timing of the last MSM (CUDA events on the context's stream, recorded only when
+ * profiling is on).  phase: 0 recode, 1 sort, 2 bucket boundaries + task list, 3 accumulate,
+ * 4 bucket/window reduction.  Returns milliseconds, or a negative value if nothing was recorded. */
+int zkp_ctx_set_profiling(zkp_ctx* ctx, int on);
+double zkp_ctx_last_phase_ms(zkp_ctx* ctx, int phase);
 const char* zkp_strerror(int status);
 
 /* ---- SRS: replaces the per-call `self.0.g1_points()` clone (kzg/src/srs.rs:78-80 at

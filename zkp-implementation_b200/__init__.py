@@ -31,6 +31,8 @@ ABI = {
     "zkp_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_ctx_set_msm_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
     "zkp_ctx_last_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "zkp_ctx_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "zkp_ctx_last_phase_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
     "zkp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "zkp_srs_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zkp_srs_upload_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
@@ -133,6 +135,18 @@ class Engine:
     def last_launches(self, kind: str) -> int:
         return int(self.lib.zkp_ctx_last_launches(self._h, 0 if kind == "msm" else 1))
 
+    def last_msm_shape(self) -> Tuple[int, int]:
+        """(window bits c, number of windows W) used by the last MSM."""
+        return int(self.lib.zkp_ctx_last_launches(self._h, 2)), int(self.lib.zkp_ctx_last_launches(self._h, 3))
+
+    PHASES = ("recode", "sort", "bounds_tasks", "accumulate", "reduce")
+
+    def set_profiling(self, on: bool) -> None:
+        self._check(self.lib.zkp_ctx_set_profiling(self._h, 1 if on else 0))
+
+    def last_phase_ms(self) -> dict:
+        return {name: float(self.lib.zkp_ctx_last_phase_ms(self._h, i)) for i, name in enumerate(self.PHASES)}
+
     # -- SRS --------------------------------------------------------------------------------------
     def srs_upload(self, xy: np.ndarray, infinity: Optional[np.ndarray] = None) -> None:
         xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 12)
@@ -223,6 +237,7 @@ class Engine:
         return w.value, l.value
 
 
+from . import dist  # noqa: E402
 from .kzg import KzgCommitment, KzgOpening, KzgScheme, Srs  # noqa: E402
 
 __all__ = ["Engine", "ZkpError", "load_library", "library_path", "ABI", "fields", "Srs", "KzgScheme",

@@ -100,7 +100,20 @@ int zkp_ctx_set_msm_window(zkp_ctx* h, uint32_t bits) {
   return ZKP_OK;
 }
 
+int zkp_ctx_set_profiling(zkp_ctx* h, int on) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  h->c.profiling = on != 0;
+  return ZKP_OK;
+}
+
+double zkp_ctx_last_phase_ms(zkp_ctx* h, int phase) {
+  if (!h || phase < 0 || phase >= Ctx::NPHASE) return -1.0;
+  return (double)h->c.phase_ms[phase];
+}
+
 int zkp_ctx_last_launches(zkp_ctx* h, int kind) {
+  if (h && kind == 2) return (int)h->c.last_window_bits;
+  if (h && kind == 3) return (int)h->c.last_windows;
   if (!h) return 0;
   return kind == 0 ? (int)h->c.msm_launches : (int)h->c.ntt_launches;
 }

@@ -80,7 +80,12 @@ struct Ctx {
   uint32_t msm_launches = 0;     // kernels launched by the last MSM (bench.py's gpu_launches)
   uint32_t ntt_launches = 0;
 
-  // last-call timing breakdown (CUDA-event free; filled only when profiling hooks are enabled)
+  // per-phase timing of the last MSM (events on `stream`; only when profiling is on)
+  static constexpr int NPHASE = 5;
+  bool profiling = false;
+  void* phase_ev[NPHASE + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float phase_ms[NPHASE] = {-1, -1, -1, -1, -1};
+  uint32_t last_window_bits = 0, last_windows = 0;
 };
 
 // ---- NTT (ntt.cu) ----

@@ -11,7 +11,8 @@
 //                  pair per digit, laid out window-major
 //   2. sort        per window radix sort of the pairs by bucket (cub::DeviceRadixSort)
 //   3. boundaries  start/end of every bucket's run in the sorted order
-//   4. tasks       buckets longer than S_max are split so no thread owns an unbounded run
+//   4. tasks       buckets longer than S_max are split so no thread owns an unbounded run; the task
+//                  list is sorted by run length (longest first) so the 32 lanes of a warp finish together
 //   5. accumulate  one thread per task: XYZZ accumulator += affine base (mixed add, 8M+2S),
 //                  next base prefetched while the current add runs
 //   6. reduce      per window: running-sum trick over segments of the bucket array, then a tree
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(256) msm_task_count_kernel(const uint32_t* __r
 __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __restrict__ bstart,
                                                              const uint32_t* __restrict__ bend,
                                                              const uint32_t* __restrict__ task_off, uint32_t total_buckets,
-                                                             uint32_t smax, MsmTask* __restrict__ tasks) {
+                                                             uint32_t smax, MsmTask* __restrict__ tasks,
+                                                             uint32_t* __restrict__ task_len, uint32_t* __restrict__ task_id) {
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb >= total_buckets) return;
   uint32_t start = bstart[gb];
@@ -123,18 +125,22 @@ __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __r
     const uint32_t len = (end - start < smax) ? (end - start) : smax;
     tasks[t].start = start;
     tasks[t].len = len;
+    task_len[t] = len;  // sort key: threads of a warp get runs of (nearly) equal length
+    task_id[t] = t;
     t++;
     start += len;
   }
 }
 
 // ---- 5. accumulate -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks, uint32_t ntasks,
+__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks,
+                                                                     const uint32_t* __restrict__ order, uint32_t ntasks,
                                                                      const uint32_t* __restrict__ svals,
                                                                      const G1Affine* __restrict__ bases,
                                                                      G1Xyzz* __restrict__ partials) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntasks) return;
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= ntasks) return;
+  const uint32_t t = order[slot];  // longest runs first; partials stay in bucket order
   const MsmTask tk = tasks[t];
   const uint32_t* v = svals + tk.start;
   G1Xyzz acc = G1Xyzz::infinity();
@@ -241,6 +247,29 @@ static int sort_window(Ctx* ctx, const uint32_t* kin, uint32_t* kout, const uint
 #endif
 }
 
+// order[] = task ids sorted by run length, longest first
+static int sort_tasks_desc(Ctx* ctx, const uint32_t* len_in, uint32_t* len_out, const uint32_t* id_in, uint32_t* id_out,
+                           uint32_t n, uint32_t key_bits) {
+#ifdef ZKP_EMU
+  (void)ctx; (void)key_bits;
+  std::vector<uint32_t> idx(n);
+  std::iota(idx.begin(), idx.end(), 0u);
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return len_in[a] > len_in[b]; });
+  for (uint32_t i = 0; i < n; i++) { len_out[i] = len_in[idx[i]]; id_out[i] = id_in[idx[i]]; }
+  return ZKP_OK;
+#else
+  size_t tmp = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, len_in, len_out, id_in, id_out, (int)n, 0,
+                                                            (int)key_bits, ctx->stream);
+  if (e != cudaSuccess) return rt::wrap(e);
+  ZKP_TRY(ctx->msm.sort_tmp.reserve(tmp));
+  tmp = ctx->msm.sort_tmp.cap;
+  e = cub::DeviceRadixSort::SortPairsDescending(ctx->msm.sort_tmp.p, tmp, len_in, len_out, id_in, id_out, (int)n, 0,
+                                                (int)key_bits, ctx->stream);
+  return rt::wrap(e);
+#endif
+}
+
 static int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
 #ifdef ZKP_EMU
   (void)ctx;
@@ -255,6 +284,35 @@ static int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint3
   tmp = ctx->msm.sort_tmp.cap;
   e = cub::DeviceScan::ExclusiveSum(ctx->msm.sort_tmp.p, tmp, in, out, (int)n, ctx->stream);
   return rt::wrap(e);
+#endif
+}
+
+static void phase_mark(Ctx* ctx, int i) {
+#ifndef ZKP_EMU
+  if (!ctx->profiling) return;
+  if (!ctx->phase_ev[i]) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->phase_ev[i] = (void*)e;
+  }
+  cudaEventRecord((cudaEvent_t)ctx->phase_ev[i], ctx->stream);
+#else
+  (void)ctx; (void)i;
+#endif
+}
+
+static void phase_collect(Ctx* ctx) {
+#ifndef ZKP_EMU
+  if (!ctx->profiling) return;
+  for (int i = 0; i < Ctx::NPHASE; i++) {
+    float ms = -1;
+    if (ctx->phase_ev[i] && ctx->phase_ev[i + 1] &&
+        cudaEventElapsedTime(&ms, (cudaEvent_t)ctx->phase_ev[i], (cudaEvent_t)ctx->phase_ev[i + 1]) != cudaSuccess)
+      ms = -1;
+    ctx->phase_ms[i] = ms;
+  }
+#else
+  (void)ctx;
 #endif
 }
 
@@ -285,7 +343,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   ZKP_TRY(m.bucket_start.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.bucket_end.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 8));
-  ZKP_TRY(m.task_meta.reserve(max_tasks * sizeof(MsmTask)));
+  ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
   ZKP_TRY(m.seg_out.reserve((size_t)nseg * nwin * sizeof(G1Xyzz)));
   ZKP_TRY(m.win_out.reserve((size_t)(nwin + 1) * sizeof(G1Xyzz)));
@@ -298,20 +356,29 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   uint32_t* ntask = m.misc.as<uint32_t>();
   uint32_t* task_off = ntask + (total_buckets + 1);
   MsmTask* tasks = m.task_meta.as<MsmTask>();
+  uint32_t* task_len = reinterpret_cast<uint32_t*>(tasks + max_tasks);
+  uint32_t* task_id = task_len + max_tasks;
+  uint32_t* task_len_sorted = task_id + max_tasks;
+  uint32_t* task_order = task_len_sorted + max_tasks;
   G1Xyzz* partials = m.partials.as<G1Xyzz>();
   G1Xyzz* seg_out = m.seg_out.as<G1Xyzz>();
   G1Xyzz* win_out = m.win_out.as<G1Xyzz>();
   cudaStream_t st = ctx->stream;
 
+  ctx->last_window_bits = c;
+  ctx->last_windows = nwin;
   // 1. recode
+  phase_mark(ctx, 0);
   ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars, n, c, nwin, keys_a, vals_a);
   ctx->msm_launches++;
+  phase_mark(ctx, 1);
   // 2. sort each window by bucket (c bits: bucket index plus the zero-digit sentinel)
   for (uint32_t w = 0; w < nwin; w++) {
     ZKP_TRY(sort_window(ctx, keys_a + (size_t)w * n, keys_b + (size_t)w * n, vals_a + (size_t)w * n,
                         vals_b + (size_t)w * n, n, c));
     ctx->msm_launches += 3;
   }
+  phase_mark(ctx, 2);
   // 3. boundaries
   ZKP_TRY(rt::dev_memset(bstart, 0, (size_t)total_buckets * 4, st));
   ZKP_TRY(rt::dev_memset(bend, 0, (size_t)total_buckets * 4, st));
@@ -328,27 +395,34 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
              ntask);
   ZKP_TRY(exclusive_scan_u32(ctx, ntask, task_off, total_buckets + 1));
   ZKP_LAUNCH(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
-             total_buckets, smax, tasks);
+             total_buckets, smax, tasks, task_len, task_id);
   ctx->msm_launches += 3;
   uint32_t ntasks = 0;
   ZKP_TRY(rt::d2h(&ntasks, task_off + total_buckets, 4, st));
   ZKP_TRY(rt::sync(st));
   // 5. accumulate
+  phase_mark(ctx, 3);
   if (ntasks) {
+    uint32_t len_bits = 1;
+    while ((1u << len_bits) <= smax) len_bits++;
+    ZKP_TRY(sort_tasks_desc(ctx, task_len, task_len_sorted, task_id, task_order, ntasks, len_bits));
     ZKP_LAUNCH(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
-               ntasks, vals_b, bases, partials);
-    ctx->msm_launches++;
+               task_order, ntasks, vals_b, bases, partials);
+    ctx->msm_launches += 3;
   }
   // 6. reduce
+  phase_mark(ctx, 4);
   ZKP_LAUNCH(msm_segment_reduce_kernel, dim3((nseg * nwin + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
              partials, task_off, ntask, nbuckets, nwin, seg_log, seg_out);
   ZKP_LAUNCH(msm_window_reduce_kernel, dim3(nwin), dim3(RED_THREADS), 0, st, seg_out, nseg, win_out);
   ctx->msm_launches += 2;
+  phase_mark(ctx, 5);
   ZKP_TRY(rt::check_last());
   // 7. host: Horner over windows
   std::vector<G1Xyzz> wins(nwin);
   ZKP_TRY(rt::d2h(wins.data(), win_out, (size_t)nwin * sizeof(G1Xyzz), st));
   ZKP_TRY(rt::sync(st));
+  phase_collect(ctx);
   G1Xyzz acc = wins[nwin - 1];
   for (int w = (int)nwin - 2; w >= 0; w--) {
     for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl(acc);
@@ -359,6 +433,10 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
 }
 
 void msm_destroy(Ctx* ctx) {
+#ifndef ZKP_EMU
+  for (int i = 0; i <= Ctx::NPHASE; i++)
+    if (ctx->phase_ev[i]) { cudaEventDestroy((cudaEvent_t)ctx->phase_ev[i]); ctx->phase_ev[i] = nullptr; }
+#endif
   MsmScratch& m = ctx->msm;
   DevBuf* all[] = {&m.scalars, &m.bases, &m.keys_a, &m.keys_b, &m.vals_a, &m.vals_b, &m.sort_tmp, &m.bucket_start,
                    &m.bucket_end, &m.task_meta, &m.partials, &m.seg_out, &m.win_out, &m.misc};

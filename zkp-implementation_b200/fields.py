@@ -69,7 +69,7 @@ def g1_from_array(arr: np.ndarray) -> List[Point]:
 
 
 def splitmix64_stream(seed: int, count: int) -> np.ndarray:
-    """`count` outputs of splitmix64 started at `seed` (vectorised; identical to oracle/pyref.SplitMix64)."""
+    """`count` outputs of splitmix64 started at `seed` (vectorised; the same generator the test oracles use)."""
     with np.errstate(over="ignore"):
         idx = np.arange(1, count + 1, dtype=np.uint64)
         z = np.uint64(seed & (2**64 - 1)) + idx * np.uint64(0x9E3779B97F4A7C15)
