@@ -75,6 +75,10 @@ ZKP_PTX3(madc_hi, "madc.hi.u32", return (uint32_t)(((uint64_t)a * b) >> 32) + c 
 // ------------------------------------------------------------------------------------------------
 struct FrParams {
   static constexpr int N = 8;
+  // r = ...ffffffff00000001: limb 0 is 1, limb 1 is 2^32 - 1 and -r^-1 = -1 (mod 2^32), so in every
+  // Montgomery reduction step m = -t0, m * r[0] is an addition and m * r[1] = (m << 32) - m is two ALU
+  // ops: 6 instead of 8 multiply-adds per step (112 instead of 128 per product).
+  static constexpr bool LOW_LIMBS_SPECIAL = true;
   static constexpr uint32_t M0 = 0xffffffffu;  // -r^-1 mod 2^32
   ZKP_HD static constexpr uint32_t mod(int i) {
     constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
@@ -95,6 +99,7 @@ struct FrParams {
 
 struct FqParams {
   static constexpr int N = 12;
+  static constexpr bool LOW_LIMBS_SPECIAL = false;
   static constexpr uint32_t M0 = 0xfffcfffdu;  // -p^-1 mod 2^32
   ZKP_HD static constexpr uint32_t mod(int i) {
     constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -237,6 +242,11 @@ ZKP_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
 }
 
 // ---- even/odd carry-chain Montgomery product (device path) ---------------------------------------
+#if defined(__CUDACC__)
+// 0xffffffff read from the constant bank at run time: keeps ptxas from treating m = -t0 as a negation
+// (it then rewrites the m * r[j] products and loses the IMAD.WIDE fusion of the reduction chain).
+static __device__ __constant__ uint32_t zkp_opaque_minus_one = 0xffffffffu;
+#endif
 namespace detail {
 // acc[j], acc[j+1] = lo, hi of a[j]*bi for even j  (n products, n even)
 template <int n>
@@ -293,10 +303,37 @@ ZKP_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_
     cmad_n<n>(even, a, bi);
     odd[n - 1] = ptx::addc(odd[n - 1], 0u);
   }
-  uint32_t mi = even[0] * P::M0;
-  cmad_n<n>(odd, mod + 1, mi);
-  cmad_n<n>(even, mod, mi);
-  odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  if constexpr (P::LOW_LIMBS_SPECIAL) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t mi = even[0] * zkp_opaque_minus_one;
+#else
+    const uint32_t mi = 0u - even[0];
+#endif
+    // odd accumulator += mi * mod[1, 3, 5, ...]; mi * (2^32 - 1) = (hi, lo) = (mi - [mi != 0], -mi)
+    const uint32_t lo1 = 0u - mi;
+    const uint32_t hi1 = mi - (mi != 0u ? 1u : 0u);
+    odd[0] = ptx::add_cc(odd[0], lo1);
+    odd[1] = ptx::addc_cc(odd[1], hi1);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+      odd[j] = ptx::madc_lo_cc(mod[j + 1], mi, odd[j]);
+      odd[j + 1] = ptx::madc_hi_cc(mod[j + 1], mi, odd[j + 1]);
+    }
+    // even accumulator += mi * mod[0, 2, 4, ...]; mi * 1 clears limb 0
+    even[0] = ptx::add_cc(even[0], mi);
+    even[1] = ptx::addc_cc(even[1], 0u);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+      even[j] = ptx::madc_lo_cc(mod[j], mi, even[j]);
+      even[j + 1] = ptx::madc_hi_cc(mod[j], mi, even[j + 1]);
+    }
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  } else {
+    const uint32_t mi = even[0] * P::M0;
+    cmad_n<n>(odd, mod + 1, mi);
+    cmad_n<n>(even, mod, mi);
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  }
 }
 }  // namespace detail
 

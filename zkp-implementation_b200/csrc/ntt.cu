@@ -26,6 +26,9 @@ static constexpr uint32_t RMAX = 9;        // largest digit of a multi-pass sche
 static constexpr uint32_t TILE_LOG = 11;   // elements per shared-memory tile (64 KB)
 static constexpr uint32_t SINGLE_MAX = 11; // largest transform done in one tile
 static constexpr uint32_t NTT_THREADS = 256;
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 2
+#endif
 
 struct NttPassArgs {
   const Fr* in;
@@ -101,7 +104,7 @@ __device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, uint32_t r, uint
   }
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(NttPassArgs a) {
   ZKP_DYN_SMEM(uint4, sm);
   const uint32_t r = a.r, q = a.q, s = a.s;
   const uint32_t E = 1u << (r + q);
@@ -240,7 +243,8 @@ int ntt_init(Ctx* ctx) {
   Fr w = fr_omega(WLOG);
   ZKP_TRY(upload_powers(ctx, &ctx->w_fwd, w, Fr::one(), (size_t)1 << (WLOG - 1)));
   ZKP_TRY(upload_powers(ctx, &ctx->w_inv, fp_inv(w), Fr::one(), (size_t)1 << (WLOG - 1)));
-  return rt::allow_smem((const void*)ntt_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr));
+  ZKP_TRY(rt::allow_smem((const void*)ntt_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr)));
+  return rt::prefer_smem_carveout((const void*)ntt_pass_kernel);  // several 64 KB tiles resident per SM
 }
 
 void ntt_destroy(Ctx* ctx) {

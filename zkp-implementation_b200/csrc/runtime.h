@@ -38,6 +38,7 @@ inline int set_device(int) { return ZKP_OK; }
 inline int device_count() { return 1; }
 inline int sm_count(int) { return 4; }
 inline int allow_smem(const void*, size_t) { return ZKP_OK; }
+inline int prefer_smem_carveout(const void*) { return ZKP_OK; }
 inline const char* last_error_string() { return "emulator"; }
 }}  // namespace zkp::rt
 #else
@@ -68,6 +69,9 @@ inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess
 inline int sm_count(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
 inline int allow_smem(const void* fn, size_t bytes) {
   return wrap(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+inline int prefer_smem_carveout(const void* fn) {
+  return wrap(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }
 inline const char* last_error_string() { return last_error_slot(); }
 }}  // namespace zkp::rt
