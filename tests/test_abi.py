@@ -18,8 +18,8 @@ def cuda_lib_path():
     return mod.build_cuda()  # nvcc cross-compiles sm_100a without a GPU
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "zkp_b200.h")).read()
+def _declared_symbols(header="zkp_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(zkp_[a-z0-9_]+)\s*\(", text)))
 
@@ -28,6 +28,15 @@ def test_header_symbols_all_exported(zkp, cuda_lib_path):
     syms = _declared_symbols()
     assert len(syms) >= 20
     assert sorted(zkp.ABI.keys()) == syms, "python binding table and header disagree"
+    lib = zkp.load_library(cuda_lib_path)
+    for s in syms:
+        assert hasattr(lib, s), s
+
+
+def test_plonk_header_symbols_all_exported(zkp, cuda_lib_path):
+    """include/zkp_plonk.h (host orchestration of the prover) ships in the same library."""
+    syms = _declared_symbols("zkp_plonk.h")
+    assert sorted(zkp.plonk.PLONK_ABI.keys()) == syms
     lib = zkp.load_library(cuda_lib_path)
     for s in syms:
         assert hasattr(lib, s), s

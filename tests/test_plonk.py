@@ -1,0 +1,138 @@
+"""The reference's PLONK prover tests (plonk/src/verifier.rs:232-382, plonk/src/challenge.rs:110-148,
+plonk/src/circuit.rs tests) restated over the drop-in mirror: the native prover (host/plonk.cpp over the
+GPU MSM + NTT) must produce the SAME proof, byte for byte, as the big-integer restatement in
+oracle/plonk_ref.py for fixed blinding scalars, and the proof must be accepted by the verifier equation.
+Runs on the CPU kernel emulator and (gpu-marked) on the B200."""
+import hashlib
+
+import pytest
+
+from oracle import plonk_ref as ref
+
+SECRET = 0x1F2E3D4C5B6A79881234567
+BLIND = [(0xABCDEF0123456789 * (i + 3) ** 7) % ref.R for i in range(9)]
+
+
+def _native_circuit(zkp, rc):
+    """Replay an oracle circuit's gates into the native builder."""
+    c = zkp.plonk.Circuit()
+    for i, g in enumerate(rc.gates):
+        wires = [(pos[0], pos[1], rc.vals[col][i]) for col, pos in enumerate((g.a, g.b, g.c))]
+        pi = (-g.pi) % ref.R
+        if g.q_m == 1:
+            c.add_multiplication_gate(*wires, pi)
+        elif g.q_r == 1:
+            c.add_addition_gate(*wires, pi)
+        else:
+            c.add_constant_gate(*wires, pi)
+    return c
+
+
+def _ref_proof_bytes(p):
+    out = b"".join(ref.g1_serialize_uncompressed(c) for c in p.commitments())
+    for s in p.scalars() + [p.u]:
+        out += int(s).to_bytes(32, "little")
+    return out + int(p.degree).to_bytes(8, "little")
+
+
+def _prove_both(zkp, engine, pyref, rc, blinding=BLIND):
+    cc_ref = rc.compile()
+    srs_pts = pyref.srs_from_secret(SECRET, cc_ref.size)
+    srs = zkp.Srs.new_from_secret(engine, SECRET, cc_ref.size)
+    assert srs.g1_points() == srs_pts
+    zkp.KzgScheme(engine, srs)  # uploads the SRS (KzgScheme::new, prover.rs:69)
+    cc = _native_circuit(zkp, rc).compile(engine)
+    assert cc.size == cc_ref.size
+    names = {"f_a": "a", "f_b": "b", "f_c": "c", "q_l": "ql", "q_r": "qr", "q_o": "qo", "q_m": "qm", "q_c": "qc", "pi": "pi"}
+    for k, rk in names.items():
+        assert cc.poly(k) == cc_ref.g[rk], k
+    for i in range(3):
+        assert cc.poly(f"s_sigma_{i + 1}") == cc_ref.sigma[i]
+    proof = zkp.plonk.generate_proof(cc, blinding)
+    want = ref.generate_proof(cc_ref, srs_pts, blinding)
+    return proof, want, cc_ref, srs_pts
+
+
+@pytest.mark.parametrize("name", ["circuit_accepted_01", "circuit_accepted_02", "circuit_accepted_03"])
+def test_reference_circuits_byte_identical(zkp, engine, pyref, name):
+    """verifier.rs:232-382 circuits: same bytes as the restated prover, and the verifier accepts."""
+    rc = getattr(ref, name)()
+    proof, want, cc_ref, srs_pts = _prove_both(zkp, engine, pyref, rc)
+    assert proof.commitments() == want.commitments()
+    assert proof.scalars() == want.scalars()
+    assert (proof.u, proof.degree) == (want.u, want.degree)
+    assert proof.to_bytes() == _ref_proof_bytes(want)
+    assert ref.verify_with_secret(cc_ref, srs_pts, SECRET, want)
+
+
+def test_wrong_witness_panics(zkp, engine, pyref):
+    """verifier.rs `circuit_accepted_01` with c = 20 instead of 25: prover.rs:404 expect("No remainder 1")."""
+    rc = ref.circuit_accepted_01(wrong=True)
+    with pytest.raises(RuntimeError, match="No remainder"):
+        ref.generate_proof(rc.compile(), pyref.srs_from_secret(SECRET, 4), BLIND)
+    srs = zkp.Srs.new_from_secret(engine, SECRET, 4)
+    zkp.KzgScheme(engine, srs)
+    cc = _native_circuit(zkp, rc).compile(engine)
+    with pytest.raises(zkp.plonk.PlonkPanic) as ei:
+        zkp.plonk.generate_proof(cc, BLIND)
+    assert ei.value.status == zkp.plonk.ERR_REMAINDER
+
+
+def _chain_circuit(n_gates, seed):
+    """alternating mul / add gates, c_i wired into a_{i+1}, random b_i."""
+    import random
+
+    rng = random.Random(seed)
+    c = ref.Circuit()
+    a = rng.randrange(ref.R)
+    for i in range(n_gates):
+        b = rng.randrange(ref.R)
+        # positions are sigma(slot): a_i <-> c_{i-1} form a 2-cycle, everything else is a fixed point
+        a_pos = (0, i) if i == 0 else (2, i - 1)
+        c_pos = (2, i) if i == n_gates - 1 else (0, i + 1)
+        out = a * b % ref.R if i % 2 == 0 else (a + b) % ref.R
+        add = c.add_multiplication_gate if i % 2 == 0 else c.add_addition_gate
+        add((a_pos[0], a_pos[1], a), (1, i, b), (c_pos[0], c_pos[1], out), 0)
+        a = out
+    return c
+
+
+@pytest.mark.parametrize("n_gates", [13, 32, 61])
+def test_chain_circuit_byte_identical(zkp, engine, pyref, n_gates):
+    rc = _chain_circuit(n_gates, seed=n_gates)
+    proof, want, cc_ref, srs_pts = _prove_both(zkp, engine, pyref, rc)
+    assert proof.to_bytes() == _ref_proof_bytes(want)
+    assert ref.verify_with_secret(cc_ref, srs_pts, SECRET, want)
+    assert proof.degree == want.degree == cc_ref.size + 1  # t has 3n + 6 coefficients -> slices of n + 2
+
+
+def test_compile_errors(zkp, engine):
+    c = zkp.plonk.Circuit()
+    c.add_addition_gate((0, 0, 1), (1, 0, 2), (2, 0, 3), 0)
+    with pytest.raises(zkp.plonk.PlonkPanic) as ei:  # circuit.rs:151 ilog2(0)
+        c.compile(engine)
+    assert ei.value.status == zkp.plonk.ERR_TOO_FEW_GATES
+    c.add_addition_gate((3, 0, 1), (1, 0, 2), (2, 0, 3), 0)
+    with pytest.raises(zkp.plonk.PlonkPanic) as ei:  # circuit.rs:221
+        c.compile(engine)
+    assert ei.value.status == zkp.plonk.ERR_INVALID_POSITION
+
+
+def test_transcript_components():
+    """challenge.rs: SHA-256 chaining, PCG32 seed expansion, ChaCha12, Fr::rand -- fixed points of the
+    restatement that do not depend on the curve: RFC 8439-style ChaCha block structure (12 rounds) and
+    the aggregation_digest_test / safe_guard behaviours."""
+    g1 = ref.o.G1
+    g2 = ref.o.g1_mul(g1, 2)
+    a = ref.ChallengeGenerator(); a.feed(g1); a.feed(g2)
+    b = ref.ChallengeGenerator(); b.feed(g2)
+    c = ref.ChallengeGenerator(); c.feed(g1); c.feed(g2)
+    ca, cb, cc_ = a.generate_challenges(3), b.generate_challenges(1), c.generate_challenges(3)
+    assert ca[0] != cb[0] and ca == cc_
+    with pytest.raises(RuntimeError, match="hungry"):
+        a.generate_challenges(3)
+    # data after one feed = SHA256(uncompressed(G)); uncompressed(G) starts with the generator's x
+    assert ref.g1_serialize_uncompressed(g1)[:4] == bytes.fromhex("17f1d3a7")
+    assert ref.g1_serialize_uncompressed(None)[0] == 0x40
+    d = ref.ChallengeGenerator(); d.feed(g1)
+    assert d.data == hashlib.sha256(ref.g1_serialize_uncompressed(g1)).digest()

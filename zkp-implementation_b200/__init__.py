@@ -237,8 +237,8 @@ class Engine:
         return w.value, l.value
 
 
-from . import dist  # noqa: E402
+from . import dist, plonk  # noqa: E402
 from .kzg import KzgCommitment, KzgOpening, KzgScheme, Srs  # noqa: E402
 
-__all__ = ["Engine", "ZkpError", "load_library", "library_path", "ABI", "fields", "Srs", "KzgScheme",
+__all__ = ["Engine", "ZkpError", "load_library", "library_path", "ABI", "fields", "plonk", "Srs", "KzgScheme",
            "KzgCommitment", "KzgOpening", "FR_MODULUS", "FQ_MODULUS"]

@@ -17,7 +17,11 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu"]
-HEADERS = ["field.cuh", "curve.cuh", "engine.h", "runtime.h"]
+HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h"]
+HOST_DIR = os.path.join(PKG, "host")
+HOST_SOURCES = ["plonk.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
+HOST_HEADERS = ["mont_host.hpp", "transcript.hpp"]
+HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-Wall"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
@@ -42,7 +46,17 @@ def _run(cmd: list[str], log: str | None = None) -> None:
 
 
 def _deps() -> list[str]:
-    return [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "zkp_b200.h")]
+    return ([os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HOST_DIR, f) for f in HOST_SOURCES + HOST_HEADERS]
+            + [os.path.join(ROOT, "include", h) for h in ("zkp_b200.h", "zkp_plonk.h")])
+
+
+def _host_objs(bdir: str) -> list[str]:
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(bdir, src.replace(".cpp", ".host.o"))
+        _run(["g++", *HOST_FLAGS, "-c", os.path.join(HOST_DIR, src), "-o", obj])
+        objs.append(obj)
+    return objs
 
 
 def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_name: str = "libzkp_b200.so") -> str:
@@ -61,7 +75,8 @@ def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_na
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs])
+    objs += _host_objs(bdir)
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp", "-o", out, *objs])
     return out
 
 
@@ -90,7 +105,8 @@ def build_emu(force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    _run(["g++", "-shared", "-pthread", "-o", out, *objs])
+    objs += _host_objs(os.path.join(edir, "_build"))
+    _run(["g++", "-shared", "-pthread", "-fopenmp", "-o", out, *objs])
     return out
 
 

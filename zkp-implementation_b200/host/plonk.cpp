@@ -1,0 +1,457 @@
+// Host orchestration of the reference's PLONK prover over the GPU engine (include/zkp_plonk.h).
+// Round structure and every formula follow plonk/src/prover.rs:61-293 and its helpers; the circuit
+// builder follows plonk/src/circuit.rs and gate.rs.  G1 sums -> zkp_msm_g1, interpolations ->
+// zkp_ntt_fr, polynomial products -> zkp_poly_mul_fr; O(n) scalar work stays on the host (OpenMP).
+#include "../../include/zkp_plonk.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <new>
+#include <vector>
+
+#include "mont_host.hpp"
+#include "transcript.hpp"
+
+using namespace zkp_host;
+typedef std::vector<Fr> Poly;
+
+namespace {
+
+struct Timers {
+  double msm = 0, ntt = 0;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  static double since(std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  }
+};
+
+// ---- ark-poly DensePolynomial semantics ---------------------------------------------------------
+void trim(Poly& p) {
+  while (!p.empty() && p.back().is_zero()) p.pop_back();
+}
+Poly add(const Poly& a, const Poly& b) {
+  const Poly& lo = a.size() < b.size() ? a : b;
+  Poly r = a.size() < b.size() ? b : a;
+#pragma omp parallel for schedule(static) if (lo.size() > 4096)
+  for (long i = 0; i < (long)lo.size(); i++) r[i] += lo[i];
+  trim(r);
+  return r;
+}
+Poly neg(const Poly& a) {
+  Poly r(a.size());
+#pragma omp parallel for schedule(static) if (a.size() > 4096)
+  for (long i = 0; i < (long)a.size(); i++) r[i] = -a[i];
+  return r;
+}
+Poly sub(const Poly& a, const Poly& b) { return add(a, neg(b)); }
+Poly scale(const Poly& a, const Fr& k) {
+  if (a.empty() || k.is_zero()) return Poly();
+  Poly r(a.size());
+#pragma omp parallel for schedule(static) if (a.size() > 4096)
+  for (long i = 0; i < (long)a.size(); i++) r[i] = a[i] * k;
+  return r;
+}
+// p + c (constant term)
+Poly add_const(Poly p, const Fr& c) {
+  if (p.empty()) p.push_back(Fr::zero());
+  p[0] += c;
+  trim(p);
+  return p;
+}
+// p * (X^n - 1)
+Poly mul_by_vanishing(const Poly& p, size_t n) {
+  if (p.empty()) return Poly();
+  Poly r(n + p.size(), Fr::zero());
+  for (size_t i = 0; i < p.size(); i++) r[n + i] = p[i];
+  for (size_t i = 0; i < p.size(); i++) r[i] -= p[i];
+  trim(r);
+  return r;
+}
+// ark-poly divide_by_vanishing_poly; returns false when the remainder is non-zero
+bool divide_by_vanishing(const Poly& a, size_t n, Poly& q) {
+  if (a.size() < n) {
+    q.clear();
+    return a.empty();
+  }
+  q.assign(a.begin() + n, a.end());
+  for (size_t i = 1; i < a.size() / n; i++) {
+    const size_t off = n * (i + 1);
+    for (size_t j = 0; off + j < a.size(); j++) q[j] += a[off + j];
+  }
+  bool zero = true;
+  for (size_t j = 0; j < n; j++) {
+    Fr r = a[j];
+    if (j < q.size()) r += q[j];
+    if (!r.is_zero()) zero = false;
+  }
+  trim(q);
+  return zero;
+}
+// Horner, chunked so that the host cores share one evaluation
+Fr eval(const Poly& p, const Fr& x) {
+  const size_t n = p.size();
+  if (n == 0) return Fr::zero();
+  const size_t chunk = 1 << 14;
+  if (n <= chunk) {
+    Fr acc = Fr::zero();
+    for (size_t i = n; i-- > 0;) acc = acc * x + p[i];
+    return acc;
+  }
+  const size_t nchunks = (n + chunk - 1) / chunk;
+  std::vector<Fr> part(nchunks);
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < (long)nchunks; c++) {
+    const size_t lo = (size_t)c * chunk, hi = std::min(n, lo + chunk);
+    Fr acc = Fr::zero();
+    for (size_t i = hi; i-- > lo;) acc = acc * x + p[i];
+    part[c] = acc;
+  }
+  const Fr xc = fr_pow(x, chunk);
+  Fr acc = Fr::zero();
+  for (size_t c = nchunks; c-- > 0;) acc = acc * xc + part[c];
+  return acc;
+}
+// a / (X - root): quotient, remainder
+Fr divide_linear(const Poly& a, const Fr& root, Poly& q) {
+  if (a.empty()) { q.clear(); return Fr::zero(); }
+  q.assign(a.size() - 1, Fr::zero());
+  Fr carry = Fr::zero();
+  for (size_t i = a.size() - 1; i >= 1; i--) {
+    carry = a[i] + carry * root;
+    q[i - 1] = carry;
+  }
+  Fr rem = a[0] + carry * root;
+  trim(q);
+  return rem;
+}
+
+// ---- engine calls -------------------------------------------------------------------------------
+int commit(zkp_ctx* ctx, const Poly& p, G1& out, Timers& tm) {
+  auto t = std::chrono::steady_clock::now();
+  uint8_t inf = 0;
+  int st = zkp_msm_g1(ctx, p.empty() ? nullptr : p[0].v, p.size(), out.xy, &inf);
+  tm.msm += Timers::since(t);
+  return st;
+}
+int commit_para(zkp_ctx* ctx, const Fr& e, G1& out, Timers& tm) {  // kzg scheme.rs:78-82: e * g1_points[0]
+  auto t = std::chrono::steady_clock::now();
+  uint8_t inf = 0;
+  int st = zkp_msm_g1(ctx, e.v, 1, out.xy, &inf);
+  tm.msm += Timers::since(t);
+  return st;
+}
+int mul(zkp_ctx* ctx, const Poly& a, const Poly& b, Poly& out, Timers& tm) {  // &a * &b
+  if (a.empty() || b.empty()) { out.clear(); return 0; }
+  auto t = std::chrono::steady_clock::now();
+  out.assign(a.size() + b.size() - 1, Fr::zero());
+  int st = zkp_poly_mul_fr(ctx, a[0].v, a.size(), b[0].v, b.size(), out[0].v);
+  tm.ntt += Timers::since(t);
+  trim(out);
+  return st;
+}
+int interpolate_batch(zkp_ctx* ctx, std::vector<Fr>& cols, uint32_t log_n, size_t batch, Timers& tm) {
+  auto t = std::chrono::steady_clock::now();
+  int st = zkp_ntt_fr(ctx, cols[0].v, log_n, batch, 1, nullptr);
+  tm.ntt += Timers::since(t);
+  return st;
+}
+
+}  // namespace
+
+// ---- circuit ------------------------------------------------------------------------------------
+struct zkp_plonk_circuit {
+  std::vector<uint8_t> kinds;
+  std::vector<uint64_t> pos;  // 6 per gate
+  std::vector<Fr> vals;       // 3 per gate
+  std::vector<Fr> pis;        // 1 per gate (as given; the gate stores -pi, gate.rs:47)
+};
+
+struct zkp_plonk_compiled {
+  size_t size = 0;
+  uint32_t log_n = 0;
+  Poly poly[12];               // f_a f_b f_c q_l q_r q_o q_m q_c pi s1 s2 s3 (trimmed coefficients)
+  std::vector<Fr> ev_abc[3];   // wire values on the domain (zero on padding rows)
+  std::vector<Fr> ev_sigma[3]; // sigma evaluations on the domain
+  Fr k1, k2, omega;
+};
+
+#define PLONK_TRY(e)                \
+  do {                              \
+    int st_ = (e);                  \
+    if (st_ != 0) return st_;       \
+  } while (0)
+
+extern "C" {
+
+zkp_plonk_circuit* zkp_plonk_circuit_new(void) { return new (std::nothrow) zkp_plonk_circuit(); }
+void zkp_plonk_circuit_free(zkp_plonk_circuit* c) { delete c; }
+size_t zkp_plonk_circuit_len(const zkp_plonk_circuit* c) { return c ? c->kinds.size() : 0; }
+
+int zkp_plonk_circuit_add_gates(zkp_plonk_circuit* c, size_t count, const uint8_t* kinds, const uint64_t* positions,
+                                const uint64_t* values, const uint64_t* pis) {
+  if (!c || (count && (!kinds || !positions || !values || !pis))) return ZKP_B200_ERR_INVALID_ARG;
+  for (size_t i = 0; i < count; i++)
+    if (kinds[i] > ZKP_PLONK_GATE_CONST) return ZKP_B200_ERR_INVALID_ARG;
+  c->kinds.insert(c->kinds.end(), kinds, kinds + count);
+  c->pos.insert(c->pos.end(), positions, positions + 6 * count);
+  const size_t v0 = c->vals.size(), p0 = c->pis.size();
+  c->vals.resize(v0 + 3 * count);
+  c->pis.resize(p0 + count);
+  memcpy(c->vals[v0].v, values, 3 * count * 32);
+  memcpy(c->pis[p0].v, pis, count * 32);
+  return 0;
+}
+
+int zkp_plonk_compile(zkp_ctx* ctx, const zkp_plonk_circuit* c, zkp_plonk_compiled** out) {
+  if (!ctx || !c || !out) return ZKP_B200_ERR_INVALID_ARG;
+  *out = nullptr;
+  const size_t ln = c->kinds.size();
+  if (ln < 2) return ZKP_PLONK_ERR_TOO_FEW_GATES;  // circuit.rs:148-157
+  uint32_t log_n = 0;
+  while (((size_t)1 << log_n) < ln) log_n++;
+  const size_t n = (size_t)1 << log_n;
+  zkp_plonk_compiled* cc = new (std::nothrow) zkp_plonk_compiled();
+  if (!cc) return ZKP_B200_ERR_OOM;
+  cc->size = n;
+  cc->log_n = log_n;
+  cc->omega = fr_omega(log_n);
+  cc->k1 = Fr::from_u64(2);  // find_cosets: roots[0] + 1, + 1 (circuit.rs:238-245)
+  cc->k2 = Fr::from_u64(3);
+  // columns 0..11 = a b c ql qr qo qm qc pi s1 s2 s3, each n long, dummy rows zero (get_assignment skips them
+  // and `interpolate` zero-pads: same vector)
+  std::vector<Fr> cols(12 * n, Fr::zero());
+  const Fr one = Fr::one(), mone = -Fr::one();
+  for (size_t i = 0; i < ln; i++) {
+    cols[0 * n + i] = c->vals[3 * i];
+    cols[1 * n + i] = c->vals[3 * i + 1];
+    cols[2 * n + i] = c->vals[3 * i + 2];
+    switch (c->kinds[i]) {
+      case ZKP_PLONK_GATE_ADD:   cols[3 * n + i] = one; cols[4 * n + i] = one; cols[5 * n + i] = mone; break;  // gate.rs:38-56
+      case ZKP_PLONK_GATE_MUL:   cols[6 * n + i] = one; cols[5 * n + i] = mone; break;                         // gate.rs:58-76
+      default:                   cols[3 * n + i] = one; cols[7 * n + i] = -c->vals[3 * i]; break;              // gate.rs:78-97
+    }
+    cols[8 * n + i] = -c->pis[i];
+  }
+  // cal_permutation (circuit.rs:200-235)
+  std::vector<Fr> roots(n);
+  roots[0] = Fr::one();
+  for (size_t i = 1; i < n; i++) roots[i] = roots[i - 1] * cc->omega;
+  const Fr ks[3] = {Fr::one(), cc->k1, cc->k2};
+  for (int col = 0; col < 3; col++)
+    for (size_t i = 0; i < n; i++) cols[(9 + col) * n + i] = roots[i] * ks[col];
+  for (size_t i = 0; i < ln; i++)
+    for (int wire = 0; wire < 3; wire++) {
+      const uint64_t pc = c->pos[6 * i + 2 * wire], pr = c->pos[6 * i + 2 * wire + 1];
+      if (pc > 2 || pr >= n) { delete cc; return ZKP_PLONK_ERR_INVALID_POSITION; }
+      cols[(9 + wire) * n + i] = roots[pr] * ks[pc];
+    }
+  for (int k = 0; k < 3; k++) {
+    cc->ev_abc[k].assign(cols.begin() + k * n, cols.begin() + (k + 1) * n);
+    cc->ev_sigma[k].assign(cols.begin() + (9 + k) * n, cols.begin() + (10 + k) * n);
+  }
+  Timers tm;
+  int st = interpolate_batch(ctx, cols, log_n, 12, tm);  // circuit.rs:173-176, 230-232
+  if (st) { delete cc; return st; }
+  for (int k = 0; k < 12; k++) {
+    cc->poly[k].assign(cols.begin() + k * n, cols.begin() + (k + 1) * n);
+    trim(cc->poly[k]);
+  }
+  *out = cc;
+  return 0;
+}
+
+void zkp_plonk_compiled_free(zkp_plonk_compiled* cc) { delete cc; }
+size_t zkp_plonk_compiled_size(const zkp_plonk_compiled* cc) { return cc ? cc->size : 0; }
+
+int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* out) {
+  if (!cc || !out || which < 0 || which > 11) return ZKP_B200_ERR_INVALID_ARG;
+  memset(out, 0, cc->size * 32);
+  if (!cc->poly[which].empty()) memcpy(out, cc->poly[which][0].v, cc->poly[which].size() * 32);
+  return 0;
+}
+
+int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                    double* timings_ms) {
+  if (!ctx || !cc || !blinding || !out) return ZKP_B200_ERR_INVALID_ARG;
+  Timers tm;
+  const size_t n = cc->size;
+  const Fr w = cc->omega;
+  Fr b[10];
+  for (int i = 1; i <= 9; i++) memcpy(b[i].v, blinding + 4 * (i - 1), 32);
+  const Poly &f_a = cc->poly[0], &f_b = cc->poly[1], &f_c = cc->poly[2], &q_l = cc->poly[3], &q_r = cc->poly[4],
+             &q_o = cc->poly[5], &q_m = cc->poly[6], &q_c = cc->poly[7], &pi = cc->poly[8], &s1 = cc->poly[9],
+             &s2 = cc->poly[10], &s3 = cc->poly[11];
+  G1 cm[9];
+
+  // ---- Round 1 (prover.rs:68-92) ----
+  auto blind2 = [&](const Fr& hi, const Fr& lo) { Poly p = {lo, hi}; trim(p); return mul_by_vanishing(p, n); };
+  const Poly ax = add(f_a, blind2(b[1], b[2]));
+  const Poly bx = add(f_b, blind2(b[3], b[4]));
+  const Poly cx = add(f_c, blind2(b[5], b[6]));
+  PLONK_TRY(commit(ctx, ax, cm[0], tm));
+  PLONK_TRY(commit(ctx, bx, cm[1], tm));
+  PLONK_TRY(commit(ctx, cx, cm[2], tm));
+
+  // ---- Round 2 (prover.rs:98-123) ----
+  ChallengeGenerator ch;
+  ch.feed(cm[0]); ch.feed(cm[1]); ch.feed(cm[2]);
+  Fr bg[2];
+  if (!ch.generate(2, bg)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  const Fr beta = bg[0], gamma = bg[1];
+  Poly pre4 = {b[9], b[8], b[7]};
+  trim(pre4);
+  pre4 = mul_by_vanishing(pre4, n);
+  Poly pre4w = {b[9], b[8] * w, b[7] * w * w};
+  trim(pre4w);
+  pre4w = mul_by_vanishing(pre4w, n);
+  // compute_acc (prover.rs:302-377) from the domain evaluations kept at compile time
+  std::vector<Fr> acc2(2 * n);
+  {
+    std::vector<Fr> num(n), den(n), roots(n);
+    roots[0] = Fr::one();
+    for (size_t i = 1; i < n; i++) roots[i] = roots[i - 1] * w;
+    const Fr bk1 = beta * cc->k1, bk2 = beta * cc->k2;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (long i = 0; i < (long)n; i++) {
+      const Fr a = cc->ev_abc[0][i] + gamma, bb = cc->ev_abc[1][i] + gamma, c = cc->ev_abc[2][i] + gamma;
+      num[i] = (a + beta * roots[i]) * (bb + bk1 * roots[i]) * (c + bk2 * roots[i]);
+      den[i] = (a + beta * cc->ev_sigma[0][i]) * (bb + beta * cc->ev_sigma[1][i]) * (c + beta * cc->ev_sigma[2][i]);
+    }
+    // batch inversion of den[0..n-2] (Montgomery's trick), then the running product
+    std::vector<Fr> pre(n);
+    Fr run = Fr::one();
+    for (size_t i = 0; i + 1 < n; i++) { pre[i] = run; run = run * den[i]; }
+    Fr inv = fr_inv(run);  // a zero denominator makes the reference's `/` panic; here it yields garbage -> remainder error
+    for (size_t i = n - 1; i-- > 0;) { const Fr di = inv * pre[i]; inv = inv * den[i]; den[i] = di; }
+    acc2[0] = Fr::one();
+    for (size_t i = 1; i < n; i++) acc2[i] = acc2[i - 1] * num[i - 1] * den[i - 1];
+    for (size_t i = 0; i < n; i++) acc2[n + i] = acc2[(i + 1) % n];  // rotate_left(1)
+  }
+  PLONK_TRY(interpolate_batch(ctx, acc2, cc->log_n, 2, tm));  // prover.rs:374-375
+  Poly acc_x(acc2.begin(), acc2.begin() + n), acc_wx(acc2.begin() + n, acc2.end());
+  trim(acc_x);
+  trim(acc_wx);
+  const Poly z_x = add(pre4, acc_x);
+  const Poly z_wx = add(pre4w, acc_wx);
+  PLONK_TRY(commit(ctx, z_x, cm[3], tm));
+
+  // ---- Round 3 (prover.rs:136-150, 381-444) ----
+  ch.feed(cm[3]);
+  Fr alpha;
+  if (!ch.generate(1, &alpha)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  Poly t1, t2, t3, quotient1, quotient23, quotient4;
+  {
+    PLONK_TRY(mul(ctx, ax, bx, t1, tm));
+    PLONK_TRY(mul(ctx, t1, q_m, t2, tm));
+    Poly line1 = t2;
+    PLONK_TRY(mul(ctx, ax, q_l, t1, tm)); line1 = add(line1, t1);
+    PLONK_TRY(mul(ctx, bx, q_r, t1, tm)); line1 = add(line1, t1);
+    PLONK_TRY(mul(ctx, cx, q_o, t1, tm)); line1 = add(line1, t1);
+    line1 = add(add(line1, pi), q_c);
+    if (!divide_by_vanishing(line1, n, quotient1)) return ZKP_PLONK_ERR_REMAINDER;  // "No remainder 1"
+  }
+  {
+    auto lin = [&](const Poly& p, const Fr& c0, const Fr& c1) { Poly l = {c0, c1}; trim(l); return add(p, l); };
+    PLONK_TRY(mul(ctx, lin(ax, gamma, beta), lin(bx, gamma, beta * cc->k1), t1, tm));
+    PLONK_TRY(mul(ctx, t1, lin(cx, gamma, beta * cc->k2), t2, tm));
+    PLONK_TRY(mul(ctx, t2, z_x, t1, tm));
+    const Poly line2 = scale(t1, alpha);
+    auto perm = [&](const Poly& p, const Poly& s) { return add_const(add(p, scale(s, beta)), gamma); };
+    PLONK_TRY(mul(ctx, perm(ax, s1), perm(bx, s2), t1, tm));
+    PLONK_TRY(mul(ctx, t1, perm(cx, s3), t2, tm));
+    PLONK_TRY(mul(ctx, t2, z_wx, t3, tm));
+    const Poly line3 = scale(t3, alpha);
+    if (!divide_by_vanishing(sub(line2, line3), n, quotient23)) return ZKP_PLONK_ERR_REMAINDER;
+  }
+  // l1_poly: interpolation of (1, 0, ..., 0) = (1/n) * sum X^i  (prover.rs:459-464)
+  Poly l1(n, fr_inv(Fr::from_u64(n)));
+  Poly zx2 = z_x;
+  if (zx2.empty()) zx2.push_back(Fr::zero());
+  zx2[0] -= Fr::one();
+  {
+    Poly zx2t = zx2;
+    trim(zx2t);
+    PLONK_TRY(mul(ctx, zx2t, l1, t1, tm));
+    if (!divide_by_vanishing(scale(t1, alpha * alpha), n, quotient4)) return ZKP_PLONK_ERR_REMAINDER;
+  }
+  const Poly tx = add(add(quotient1, quotient23), quotient4);
+  // SlicePoly::new (slice_polynomial.rs:22-43)
+  size_t tmp = tx.size() / 3;
+  if (tmp * 3 < tx.size()) tmp++;
+  Poly slices[3];
+  for (int i = 0; i < 3 && tmp; i++) {
+    const size_t lo = std::min(tx.size(), (size_t)i * tmp), hi = std::min(tx.size(), (size_t)(i + 1) * tmp);
+    slices[i].assign(tx.begin() + lo, tx.begin() + hi);
+    trim(slices[i]);
+  }
+  const uint64_t degree = (uint64_t)tmp - 1;  // wraps like the reference's usize arithmetic would panic; tmp >= 1 for valid circuits
+  for (int i = 0; i < 3; i++) PLONK_TRY(commit(ctx, slices[i], cm[4 + i], tm));
+
+  // ---- Round 4 (prover.rs:156-178) ----
+  ch.feed(cm[4]); ch.feed(cm[5]); ch.feed(cm[6]);
+  Fr zeta;
+  if (!ch.generate(1, &zeta)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  const Fr bar_a = eval(ax, zeta), bar_b = eval(bx, zeta), bar_c = eval(cx, zeta);
+  const Fr bar_s1 = eval(s1, zeta), bar_s2 = eval(s2, zeta);
+  const Fr bar_z_w = eval(z_x, zeta * w);
+  const Fr pi_e = eval(pi, zeta);
+  Poly tx_compact;
+  for (int i = 0; i < 3; i++) tx_compact = add(tx_compact, scale(slices[i], fr_pow(zeta, (degree + 1) * (uint64_t)i)));
+
+  // ---- Round 5 (prover.rs:183-272) ----
+  const Fr bars[6] = {bar_a, bar_b, bar_c, bar_s1, bar_s2, bar_z_w};
+  for (int i = 0; i < 6; i++) {
+    G1 e;
+    PLONK_TRY(commit_para(ctx, bars[i], e, tm));
+    ch.feed(e);
+  }
+  Fr v;
+  if (!ch.generate(1, &v)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  // compute_linearisation_polynomial (prover.rs:469-568; the self-check products are not recomputed)
+  Poly line1 = add(add(add(add(scale(q_m, bar_a * bar_b), scale(q_l, bar_a)), scale(q_r, bar_b)), scale(q_o, bar_c)), q_c);
+  line1 = add_const(line1, pi_e);
+  const Fr sc2 = (bar_a + beta * zeta + gamma) * (bar_b + beta * cc->k1 * zeta + gamma) * (bar_c + beta * cc->k2 * zeta + gamma) * alpha;
+  const Poly line2 = scale(z_x, sc2);
+  const Fr sc3 = (bar_a + beta * bar_s1 + gamma) * (bar_b + beta * bar_s2 + gamma) * bar_z_w * alpha;
+  const Poly line3 = scale(add_const(scale(s3, beta), bar_c + gamma), sc3);
+  const Fr z_h_e = fr_pow(zeta, n) - Fr::one();
+  const Fr l1_e = eval(l1, zeta);
+  Poly zx2t = zx2;
+  trim(zx2t);
+  const Poly line4 = scale(zx2t, l1_e * alpha * alpha);
+  const Poly line5 = scale(tx_compact, z_h_e);
+  const Poly r_x = add(add(add(add(line1, line2), neg(line3)), line4), neg(line5));
+  const Fr bar_r = eval(r_x, zeta);
+  auto sub_para = [&](const Poly& p, const Fr& k) { return add_const(p, -k); };
+  const Fr v2 = v * v, v3 = v2 * v, v4 = v3 * v, v5 = v4 * v;
+  Poly wx = sub_para(r_x, bar_r);
+  wx = add(wx, scale(sub_para(ax, bar_a), v));
+  wx = add(wx, scale(sub_para(bx, bar_b), v2));
+  wx = add(wx, scale(sub_para(cx, bar_c), v3));
+  wx = add(wx, scale(sub_para(s1, bar_s1), v4));
+  wx = add(wx, scale(sub_para(s2, bar_s2), v5));
+  Poly w_ev_x, w_ev_wx;
+  if (!divide_linear(wx, zeta, w_ev_x).is_zero()) return ZKP_PLONK_ERR_REMAINDER;            // prover.rs:228-240
+  if (!divide_linear(sub_para(z_x, bar_z_w), zeta * w, w_ev_wx).is_zero()) return ZKP_PLONK_ERR_REMAINDER;  // :248-260
+  PLONK_TRY(commit(ctx, w_ev_x, cm[7], tm));
+  PLONK_TRY(commit(ctx, w_ev_wx, cm[8], tm));
+  ch.feed(cm[7]); ch.feed(cm[8]);
+  Fr u;
+  if (!ch.generate(1, &u)) return ZKP_PLONK_ERR_TRANSCRIPT;
+
+  for (int i = 0; i < 9; i++) memcpy(out->commitments[i], cm[i].xy, 96);
+  for (int i = 0; i < 6; i++) memcpy(out->evaluations[i], bars[i].v, 32);
+  memcpy(out->u, u.v, 32);
+  out->degree = degree;
+  if (timings_ms) {
+    timings_ms[0] = Timers::since(tm.t0);
+    timings_ms[1] = tm.msm;
+    timings_ms[2] = tm.ntt;
+    timings_ms[3] = timings_ms[0] - tm.msm - tm.ntt;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's `plonk` crate surface for the hot path, over the C ABI in
+``include/zkp_plonk.h`` (implemented by ``host/plonk.cpp`` inside ``libzkp_b200.so``).
+
+=====================================================  =======================================
+reference (plonk/src)                                  here
+=====================================================  =======================================
+``Circuit::default`` / ``add_*_gate``  circuit.rs:85   :class:`Circuit`
+``Circuit::compile``               circuit.rs:166-197  :meth:`Circuit.compile`
+``CompiledCircuit``             compiled_circuit.rs:5  :class:`CompiledCircuit`
+``prover::generate_proof``          prover.rs:61-293   :func:`generate_proof`
+``prover::Proof``                   prover.rs:24-58    :class:`Proof`
+=====================================================  =======================================
+
+Wires are ``(column, row, value)`` triples exactly as in the reference.  Field values are Python ints
+(canonical).  The nine blinding scalars the reference draws from ``StdRng::from_entropy()``
+(prover.rs:68) are an explicit argument, which is what makes proofs reproducible byte for byte.
+Every G1 sum and every transform of `generate_proof` runs on the GPU engine the scheme was built on;
+this file only marshals arguments.  No arithmetic fallback lives here.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import fields
+from .fields import FR_MODULUS
+
+Point = Optional[Tuple[int, int]]
+Wire = Tuple[int, int, int]
+
+ERR_REMAINDER, ERR_INVALID_POSITION, ERR_TOO_FEW_GATES, ERR_TRANSCRIPT = 20, 21, 22, 23
+
+_vp = ctypes.c_void_p
+PLONK_ABI = {
+    "zkp_plonk_circuit_new": (_vp, []),
+    "zkp_plonk_circuit_free": (None, [_vp]),
+    "zkp_plonk_circuit_add_gates": (ctypes.c_int, [_vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]),
+    "zkp_plonk_circuit_len": (ctypes.c_size_t, [_vp]),
+    "zkp_plonk_compile": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "zkp_plonk_compiled_free": (None, [_vp]),
+    "zkp_plonk_compiled_size": (ctypes.c_size_t, [_vp]),
+    "zkp_plonk_compiled_poly": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "zkp_plonk_prove": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+}
+
+_PANICS = {
+    ERR_REMAINDER: "No remainder here",                                  # prover.rs:404/431/441
+    ERR_INVALID_POSITION: "Invalid position",                             # circuit.rs:221
+    ERR_TOO_FEW_GATES: "argument of integer logarithm must be positive",  # circuit.rs:151
+    ERR_TRANSCRIPT: "I'm hungry! Feed me something first",                # challenge.rs:61-63
+}
+
+
+class PlonkPanic(RuntimeError):
+    """A status where the reference panics; ``status`` is the ZKP_PLONK_ERR_* / ZKP_B200_ERR_* code."""
+
+    def __init__(self, status: int, msg: str):
+        super().__init__(msg)
+        self.status = status
+
+
+def _bind(lib) -> None:
+    if getattr(lib, "_plonk_bound", False):
+        return
+    for name, (res, args) in PLONK_ABI.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._plonk_bound = True
+
+
+def _raise(engine, st: int) -> None:
+    if st == 0:
+        return
+    msg = _PANICS.get(st) or engine.lib.zkp_strerror(st).decode()
+    raise PlonkPanic(st, msg)
+
+
+POLY_NAMES = ("f_a", "f_b", "f_c", "q_l", "q_r", "q_o", "q_m", "q_c", "pi", "s_sigma_1", "s_sigma_2", "s_sigma_3")
+
+
+class Circuit:
+    """plonk/src/circuit.rs:17-115.  Gates are buffered here and handed to the native builder in bulk."""
+
+    ADD, MUL, CONST = 0, 1, 2
+
+    def __init__(self):
+        self._kinds: List[int] = []
+        self._pos: List[int] = []
+        self._vals: List[int] = []
+        self._pis: List[int] = []
+
+    def _add(self, a: Wire, b: Wire, c: Wire, kind: int, pi: int) -> None:
+        for w in (a, b, c):
+            if w[0] < 0 or w[1] < 0:
+                raise OverflowError("usize position")
+            self._pos += [int(w[0]), int(w[1])]
+            self._vals.append(int(w[2]) % FR_MODULUS)
+        self._kinds.append(kind)
+        self._pis.append(int(pi) % FR_MODULUS)
+
+    def add_addition_gate(self, a: Wire, b: Wire, c: Wire, pi: int = 0) -> None:
+        self._add(a, b, c, self.ADD, pi)
+
+    def add_multiplication_gate(self, a: Wire, b: Wire, c: Wire, pi: int = 0) -> None:
+        self._add(a, b, c, self.MUL, pi)
+
+    def add_constant_gate(self, a: Wire, b: Wire, c: Wire, pi: int = 0) -> None:
+        self._add(a, b, c, self.CONST, pi)
+
+    def add_gates_bulk(self, kinds: np.ndarray, positions: np.ndarray, values_mont: np.ndarray, pis_mont: np.ndarray):
+        """Large synthetic circuits: arrays already in ABI layout (count; count x 6; count x 3 x 4; count x 4)."""
+        self._bulk = (np.ascontiguousarray(kinds, dtype=np.uint8), np.ascontiguousarray(positions, dtype=np.uint64),
+                      np.ascontiguousarray(values_mont, dtype=np.uint64), np.ascontiguousarray(pis_mont, dtype=np.uint64))
+
+    def __len__(self) -> int:
+        return len(self._kinds) + (len(self._bulk[0]) if getattr(self, "_bulk", None) else 0)
+
+    def compile(self, engine) -> "CompiledCircuit":
+        """circuit.rs:166-197: pad to a power of two, interpolate the nine gate columns and the three
+        sigma columns (one batched iNTT on the GPU)."""
+        lib = engine.lib
+        _bind(lib)
+        h = lib.zkp_plonk_circuit_new()
+        if not h:
+            raise MemoryError
+        try:
+            if self._kinds:
+                kinds = np.array(self._kinds, dtype=np.uint8)
+                pos = np.array(self._pos, dtype=np.uint64)
+                vals = fields.fr_to_mont_array(self._vals)
+                pis = fields.fr_to_mont_array(self._pis)
+                _raise(engine, lib.zkp_plonk_circuit_add_gates(h, len(kinds), kinds.ctypes.data, pos.ctypes.data,
+                                                               vals.ctypes.data, pis.ctypes.data))
+            if getattr(self, "_bulk", None):
+                k, p, v, q = self._bulk
+                _raise(engine, lib.zkp_plonk_circuit_add_gates(h, len(k), k.ctypes.data, p.ctypes.data, v.ctypes.data,
+                                                               q.ctypes.data))
+            out = _vp()
+            _raise(engine, lib.zkp_plonk_compile(engine._h, h, ctypes.byref(out)))
+            return CompiledCircuit(engine, out)
+        finally:
+            lib.zkp_plonk_circuit_free(h)
+
+
+class CompiledCircuit:
+    """plonk/src/compiled_circuit.rs:5-42 (gate + copy constraints as coefficient vectors)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self._h = handle
+        self.size = int(engine.lib.zkp_plonk_compiled_size(handle))
+
+    def poly(self, name: str) -> List[int]:
+        """Trimmed coefficients (canonical ints) of one compiled polynomial; names as in constraint.rs."""
+        buf = np.zeros((self.size, 4), dtype=np.uint64)
+        _raise(self.engine, self.engine.lib.zkp_plonk_compiled_poly(self._h, POLY_NAMES.index(name), buf.ctypes.data))
+        c = fields.fr_from_mont_array(buf)
+        while c and c[-1] == 0:
+            c.pop()
+        return c
+
+    def close(self) -> None:
+        if self._h:
+            self.engine.lib.zkp_plonk_compiled_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _ProofStruct(ctypes.Structure):
+    _fields_ = [("commitments", ctypes.c_uint64 * 12 * 9), ("evaluations", ctypes.c_uint64 * 4 * 6),
+                ("u", ctypes.c_uint64 * 4), ("degree", ctypes.c_uint64)]
+
+
+@dataclass
+class Proof:
+    """plonk/src/prover.rs:24-58."""
+
+    a_commit: Point
+    b_commit: Point
+    c_commit: Point
+    z_commit: Point
+    t_lo_commit: Point
+    t_mid_commit: Point
+    t_hi_commit: Point
+    w_ev_x_commit: Point
+    w_ev_wx_commit: Point
+    bar_a: int
+    bar_b: int
+    bar_c: int
+    bar_s_sigma_1: int
+    bar_s_sigma_2: int
+    bar_z_w: int
+    u: int
+    degree: int
+    timings_ms: Optional[dict] = None
+
+    def commitments(self) -> List[Point]:
+        return [self.a_commit, self.b_commit, self.c_commit, self.z_commit, self.t_lo_commit, self.t_mid_commit,
+                self.t_hi_commit, self.w_ev_x_commit, self.w_ev_wx_commit]
+
+    def scalars(self) -> List[int]:
+        return [self.bar_a, self.bar_b, self.bar_c, self.bar_s_sigma_1, self.bar_s_sigma_2, self.bar_z_w]
+
+    def to_bytes(self) -> bytes:
+        """Canonical byte string of the proof for byte-for-byte comparison: the nine commitments in
+        ark-serialize's uncompressed G1 layout (what the transcript hashes, challenge.rs:52-55), the six
+        evaluations and u as 32-byte little-endian canonical Fr, the degree as u64 LE."""
+        out = b""
+        for p in self.commitments():
+            out += (bytes([0x40]) + bytes(95)) if p is None else p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+        for s in self.scalars() + [self.u]:
+            out += int(s).to_bytes(32, "little")
+        return out + int(self.degree).to_bytes(8, "little")
+
+
+def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int]) -> Proof:
+    """prover.rs:61-293 against the SRS resident on the compiled circuit's engine (`KzgScheme(engine, srs)`
+    uploads it).  ``blinding`` = b1..b9."""
+    eng = compiled_circuit.engine
+    _bind(eng.lib)
+    if len(blinding) != 9:
+        raise ValueError("blinding must hold b1..b9")
+    b = fields.fr_to_mont_array(blinding)
+    ps = _ProofStruct()
+    tm = (ctypes.c_double * 4)()
+    _raise(eng, eng.lib.zkp_plonk_prove(eng._h, compiled_circuit._h, b.ctypes.data, ctypes.addressof(ps),
+                                        ctypes.addressof(tm)))
+    cm = fields.g1_from_array(np.frombuffer(bytes(ps.commitments), dtype=np.uint64).reshape(9, 12))
+    ev = fields.fr_from_mont_array(np.frombuffer(bytes(ps.evaluations), dtype=np.uint64).reshape(6, 4))
+    u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
+    return Proof(*cm, *ev, u, int(ps.degree),
+                 timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "host": tm[3]})
