@@ -431,12 +431,15 @@ def generate_proof(cc: CompiledCircuit, srs, blinding: Sequence[int]) -> Proof:
 
 
 # ----------------------------------------------------------------------------- verifier (verifier.rs) under a known secret
-def verify_with_secret(cc: CompiledCircuit, srs, secret: int, proof: Proof) -> bool:
+def verify_with_secret(cc: CompiledCircuit, srs, secret: int, proof: Proof, commit_fn=None) -> bool:
+    """`commit_fn(coeffs) -> point` replaces the big-integer MSM for the eight preprocessed commitments
+    (verifier.rs:173-180) when the circuit is too large for it (the GPU tests pass the engine's commit)."""
     n = cc.size
     w = o.root_of_unity(n)
     mul, add, neg = o.g1_mul, o.g1_add, o.g1_neg
-    q_m, q_l, q_r, q_o, q_c = (commit(cc.g[k], srs) for k in ("qm", "ql", "qr", "qo", "qc"))
-    s1, s2, s3 = (commit(s, srs) for s in cc.sigma)
+    cm = commit_fn or (lambda poly: commit(poly, srs))
+    q_m, q_l, q_r, q_o, q_c = (cm(cc.g[k]) for k in ("qm", "ql", "qr", "qo", "qc"))
+    s1, s2, s3 = (cm(s) for s in cc.sigma)
     # verify_challenges (:188-220)
     ch = ChallengeGenerator()
     ch.feed(proof.a); ch.feed(proof.b); ch.feed(proof.c)

@@ -239,3 +239,34 @@ def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int]) -
     u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
     return Proof(*cm, *ev, u, int(ps.degree),
                  timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "host": tm[3]})
+
+
+def chain_circuit(n_gates: int, seed: int) -> Circuit:
+    """Synthetic workload of SURVEY.md 8d config 4: n_gates alternating multiplication / addition gates,
+    the output of gate i wired into the left input of gate i + 1 (a 2-cycle in the permutation), random
+    right inputs.  Deterministic in (n_gates, seed).  Built directly in ABI layout (Montgomery limbs)."""
+    import random
+
+    rng = random.Random(seed)
+    R = FR_MODULUS
+    vals: List[int] = []
+    a = rng.randrange(R)
+    for i in range(n_gates):
+        b = rng.getrandbits(254)
+        out = a * b % R if i % 2 == 0 else (a + b) % R
+        vals += [a, b, out]
+        a = out
+    idx = np.arange(n_gates, dtype=np.uint64)
+    pos = np.zeros((n_gates, 6), dtype=np.uint64)
+    pos[:, 0] = 2                      # a_i  -> slot of c_{i-1}
+    pos[:, 1] = idx - np.uint64(1)
+    pos[0, 0], pos[0, 1] = 0, 0        # first gate: fixed point
+    pos[:, 2], pos[:, 3] = 1, idx      # b_i: fixed point
+    pos[:, 4] = 0                      # c_i  -> slot of a_{i+1}
+    pos[:, 5] = idx + np.uint64(1)
+    pos[-1, 4], pos[-1, 5] = 2, n_gates - 1
+    kinds = np.where(idx % 2 == 0, Circuit.MUL, Circuit.ADD).astype(np.uint8)
+    c = Circuit()
+    c.add_gates_bulk(kinds, pos, fields.fr_to_mont_array(vals).reshape(n_gates, 3, 4),
+                     np.zeros((n_gates, 4), dtype=np.uint64))
+    return c
