@@ -104,6 +104,28 @@ int zkp_poly_mul_fr(zkp_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* 
 /* a[i] *= b[i] on device vectors (the pointwise step of a product kept resident). */
 int zkp_fr_mul_pointwise_dev(zkp_ctx* ctx, void* a_dev, const void* b_dev, size_t n);
 
+/* ---- multi-GPU four-step NTT (one process per GPU).  N = 2^r x 2^(log_n - r),
+ *      r = zkp_ntt_dist_rows_log.  Rank g of G holds
+ *        layout A:  a[j1][c]  = x[j1 * 2^(log_n-r) + g * 2^(log_n-r)/G + c]   (its column block, row-major)
+ *        layout B:  b[k'][k2] = X[(g * 2^r/G + k') + 2^r * k2]                (its rows of the result)
+ *      forward: A -> stage (column transforms + omega_N^(col*k) twiddles) -> all-to-all -> local batched
+ *      transforms of size 2^(log_n-r) (zkp_ntt_fr_dev, batch 2^r/G) -> B.   inverse: B -> A, the exact
+ *      reverse.  The all-to-all is either NCCL (stage in place, then zkp_ntt_dist_permute_dev around the
+ *      collective) or fused into the stage kernel: with `peer_bufs` (G device pointers, one exchange buffer
+ *      of N/G elements per rank, opened with the zkp_ipc_* calls) the forward stage stores each row
+ *      straight into its owner's buffer over NVLink and the inverse stage loads from them. ------------- */
+uint32_t zkp_ntt_dist_rows_log(uint32_t log_n, uint32_t world);
+int zkp_ntt_dist_stage_dev(zkp_ctx* ctx, void* data_dev, uint32_t log_n, uint32_t rank, uint32_t world, int inverse,
+                           const uint64_t* coset_offset, void* const* peer_bufs);
+int zkp_ntt_dist_permute_dev(zkp_ctx* ctx, const void* in_dev, void* out_dev, uint32_t log_n, uint32_t world, int inverse);
+/* Exchange buffers: plain device allocations whose CUDA IPC handle (64 bytes) is handed to the peer processes. */
+int zkp_dev_alloc(zkp_ctx* ctx, size_t bytes, void** out_dev);
+int zkp_dev_free(zkp_ctx* ctx, void* dev);
+int zkp_dev_copy(zkp_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes); /* device-to-device, on the context's stream */
+int zkp_ipc_export(zkp_ctx* ctx, const void* dev, uint8_t handle[64]);
+int zkp_ipc_open(zkp_ctx* ctx, const uint8_t handle[64], void** out_dev);
+int zkp_ipc_close(zkp_ctx* ctx, void* dev);
+
 /* ---- synthetic workloads (bench configs 2/5): n distinct pseudo-random G1 points generated on
  *      the device from a seed (a0 + i*delta) * G, affine, written to bases_dev (n x 96 B). ----- */
 int zkp_g1_generate_bases_dev(zkp_ctx* ctx, uint64_t seed, size_t n, void* bases_dev);

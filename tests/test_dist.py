@@ -67,3 +67,56 @@ def test_shard_ranges(zkp):
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+
+
+def _ntt_worker(rank, world, port, emu_path, log_n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    import zkp_implementation_b200 as z
+    from oracle import coracle as c
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    F = z.fields
+    eng = z.Engine(0, lib_path=emu_path)
+    n = 1 << log_n
+    x = F.random_fr_mont(900 + log_n, n)
+    d = z.dist.DistNtt(eng, log_n, rank, world)
+    ok = []
+    for coset in (None, 7):
+        cs = None if coset is None else F.fr_to_mont_array([coset])[0]
+        want = c.ntt(x, log_n, coset_mont=cs) if coset else c.ntt(x, log_n)
+        a = torch.from_numpy(d.layout_a(x).view(np.int64).reshape(-1).copy())
+        b = d.forward(a, coset=coset)
+        ok.append(bool((b.numpy().view(np.uint64).reshape(-1, 4) == d.layout_b(want)).all()))
+        back = d.inverse(b, coset=coset)
+        ok.append(bool((back.numpy().view(np.uint64).reshape(-1, 4) == d.layout_a(x)).all()))
+    q.put((rank, all(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 6), (2, 13), (4, 9)])
+def test_four_step_ntt_gloo(zkp, world, log_n):
+    """Distributed four-step NTT (stage kernel + all-to-all + local batched NTT) == single NTT of the oracle,
+    forward / inverse / coset, on the kernel emulator with gloo."""
+    import importlib.util
+    import torch.multiprocessing as mp
+
+    from oracle import coracle
+    coracle.build()
+    spec = importlib.util.spec_from_file_location("zkp_b200_build", os.path.join(ROOT, "zkp-implementation_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    emu = mod.build_emu()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world * 7 + log_n) % 2000
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, emu, log_n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]

@@ -53,6 +53,17 @@ ABI = {
     "zkp_poly_mul_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_fr_mul_pointwise_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_ntt_dist_rows_log": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
+    "zkp_ntt_dist_stage_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_ntt_dist_permute_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
+                                                ctypes.c_uint32, ctypes.c_int]),
+    "zkp_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "zkp_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_dev_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_ipc_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "zkp_ipc_close": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_g1_generate_bases_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_bench_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
@@ -226,6 +237,48 @@ class Engine:
 
     def mul_pointwise_dev(self, a_dev, b_dev, n: int) -> None:
         self._check(self.lib.zkp_fr_mul_pointwise_dev(self._h, _ptr(a_dev), _ptr(b_dev), n))
+
+    # -- multi-GPU four-step NTT (see dist.DistNtt) ------------------------------------------------
+    def ntt_dist_rows_log(self, log_n: int, world: int) -> int:
+        return int(self.lib.zkp_ntt_dist_rows_log(log_n, world))
+
+    def ntt_dist_stage_dev(self, data_dev, log_n: int, rank: int, world: int, inverse: bool = False,
+                           coset: Optional[int] = None, peers: Optional[Sequence[int]] = None) -> None:
+        cs = None if coset is None else fields.fr_to_mont_array([coset])
+        arr = None
+        if peers is not None:
+            arr = (ctypes.c_void_p * len(peers))(*[ctypes.c_void_p(int(p)) for p in peers])
+        self._check(self.lib.zkp_ntt_dist_stage_dev(self._h, _ptr(data_dev), log_n, rank, world, 1 if inverse else 0,
+                                                    _ptr(cs), ctypes.cast(arr, ctypes.c_void_p) if arr is not None else None))
+
+    def ntt_dist_permute_dev(self, in_dev, out_dev, log_n: int, world: int, inverse: bool = False) -> None:
+        self._check(self.lib.zkp_ntt_dist_permute_dev(self._h, _ptr(in_dev), _ptr(out_dev), log_n, world,
+                                                      1 if inverse else 0))
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.lib.zkp_dev_alloc(self._h, nbytes, ctypes.byref(p)))
+        return int(p.value or 0)
+
+    def dev_free(self, ptr: int) -> None:
+        self._check(self.lib.zkp_dev_free(self._h, ctypes.c_void_p(ptr)))
+
+    def dev_copy(self, dst, src, nbytes: int) -> None:
+        self._check(self.lib.zkp_dev_copy(self._h, _ptr(dst), _ptr(src), nbytes))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.zkp_ipc_export(self._h, ctypes.c_void_p(ptr), ctypes.cast(buf, ctypes.c_void_p)))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (ctypes.c_uint8 * 64)(*handle)
+        p = ctypes.c_void_p()
+        self._check(self.lib.zkp_ipc_open(self._h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(p)))
+        return int(p.value or 0)
+
+    def ipc_close(self, ptr: int) -> None:
+        self._check(self.lib.zkp_ipc_close(self._h, ctypes.c_void_p(ptr)))
 
     # -- synthetic workloads / microbenchmarks ----------------------------------------------------
     def generate_bases_dev(self, seed: int, n: int, bases_dev) -> None:

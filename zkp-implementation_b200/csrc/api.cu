@@ -308,6 +308,81 @@ int zkp_poly_mul_fr(zkp_ctx* h, const uint64_t* a, size_t la, const uint64_t* b,
   return rt::sync(c->stream);
 }
 
+// ---- multi-GPU four-step NTT ---------------------------------------------------------------------
+static int world_log_of(uint32_t world, uint32_t* wl) {
+  uint32_t l = 0;
+  while ((1u << l) < world) l++;
+  if (world == 0 || (1u << l) != world || l > 3) return ZKP_ERR_INVALID_ARG;
+  *wl = l;
+  return ZKP_OK;
+}
+
+uint32_t zkp_ntt_dist_rows_log(uint32_t log_n, uint32_t world) {
+  uint32_t wl;
+  if (world_log_of(world, &wl) != ZKP_OK) return 0;
+  return ntt_dist_rows_log(log_n, wl);
+}
+
+int zkp_ntt_dist_stage_dev(zkp_ctx* h, void* data_dev, uint32_t log_n, uint32_t rank, uint32_t world, int inverse,
+                           const uint64_t* coset, void* const* peer_bufs) {
+  if (!h || !data_dev) return ZKP_ERR_INVALID_ARG;
+  uint32_t wl;
+  ZKP_TRY(world_log_of(world, &wl));
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  Fr hh;
+  if (coset) memcpy(hh.v, coset, 32);
+  return ntt_dist_stage_dev(&h->c, (Fr*)data_dev, log_n, rank, wl, inverse != 0, coset ? &hh : nullptr,
+                            (Fr* const*)peer_bufs);
+}
+
+int zkp_ntt_dist_permute_dev(zkp_ctx* h, const void* in_dev, void* out_dev, uint32_t log_n, uint32_t world, int inverse) {
+  if (!h || !in_dev || !out_dev) return ZKP_ERR_INVALID_ARG;
+  uint32_t wl;
+  ZKP_TRY(world_log_of(world, &wl));
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return ntt_dist_permute_dev(&h->c, (const Fr*)in_dev, (Fr*)out_dev, log_n, wl, inverse != 0);
+}
+
+int zkp_dev_alloc(zkp_ctx* h, size_t bytes, void** out_dev) {
+  if (!h || !out_dev) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::dev_malloc(out_dev, bytes);
+}
+
+int zkp_dev_free(zkp_ctx* h, void* dev) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  rt::sync(h->c.stream);
+  rt::dev_free(dev);
+  return ZKP_OK;
+}
+
+int zkp_dev_copy(zkp_ctx* h, void* dst_dev, const void* src_dev, size_t bytes) {
+  if (!h || (bytes && (!dst_dev || !src_dev))) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::d2d(dst_dev, src_dev, bytes, h->c.stream);
+}
+
+int zkp_ipc_export(zkp_ctx* h, const void* dev, uint8_t handle[64]) {
+  if (!h || !dev || !handle) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::ipc_export(dev, handle);
+}
+
+int zkp_ipc_open(zkp_ctx* h, const uint8_t handle[64], void** out_dev) {
+  if (!h || !handle || !out_dev) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::ipc_open(handle, out_dev);
+}
+
+int zkp_ipc_close(zkp_ctx* h, void* dev) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::ipc_close(dev);
+}
+
 // ---- synthetic workloads / microbenchmarks ------------------------------------------------------
 int zkp_g1_generate_bases_dev(zkp_ctx* h, uint64_t seed, size_t n, void* bases_dev) {
   if (!h || (n && !bases_dev)) return ZKP_ERR_INVALID_ARG;

@@ -94,6 +94,11 @@ void ntt_destroy(Ctx* ctx);
 // In-place batched transform on device memory.  coset == nullptr -> plain domain.
 int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, const Fr* coset_host);
 int fr_pointwise_mul_dev(Ctx* ctx, Fr* a, const Fr* b, size_t n);  // a[i] *= b[i]
+// Distributed four-step transform, one stage per call (the all-to-all sits between them; see ntt.cu)
+uint32_t ntt_dist_rows_log(uint32_t log_n, uint32_t world_log);
+int ntt_dist_stage_dev(Ctx* ctx, Fr* data, uint32_t log_n, uint32_t rank, uint32_t world_log, bool inverse,
+                       const Fr* coset_host, Fr* const* peers);
+int ntt_dist_permute_dev(Ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, uint32_t world_log, bool inverse);
 
 // ---- MSM (msm.cu) ----
 // result: W window sums are reduced on the device; the final Horner over windows and the single

@@ -50,6 +50,20 @@ struct NttPassArgs {
   size_t batch_stride;
 };
 
+// Distributed four-step transform: the first stage of the forward transform (last stage of
+// the inverse) is this same pass kernel run on the rank's column block of the 2^r x 2^s_glob matrix.
+// The twiddle / coset exponents use GLOBAL column indices; rows can be pushed to (forward) or pulled from
+// (inverse) the exchange buffers of the peer GPUs over NVLink, which fuses the all-to-all transpose into
+// the kernel's store / load loop.  Exchange-buffer layout on every rank: [row'][global column].
+struct NttDistArgs {
+  uint32_t s_glob;      // log_n - r
+  uint32_t col_off;     // global index of local column 0
+  uint32_t tw_on_load;  // inverse stage: multiply by omega^-(col * k) while loading row k
+  uint32_t peer_log;    // rows owned by one peer = 2^peer_log
+  uint32_t push, pull;
+  Fr* peer[8];
+};
+
 // Shared-memory tile: two planes of 16-byte halves so that consecutive lanes touch consecutive
 // 16-byte words (conflict-free for unit-stride element access).
 __device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i) {
@@ -104,7 +118,8 @@ __device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, uint32_t r, uint
   }
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(NttPassArgs a) {
+template <bool DIST>
+__device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDistArgs* dd) {
   ZKP_DYN_SMEM(uint4, sm);
   const uint32_t r = a.r, q = a.q, s = a.s;
   const uint32_t E = 1u << (r + q);
@@ -132,10 +147,34 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(N
   // ---- load (optionally scaled by the coset powers h^addr) ----
   for (uint32_t idx = tid; idx < E; idx += nthreads) {
     uint32_t addr, sidx;
+    const Fr* src = in;
+    uint32_t tw_k = 0, tw_col = 0;
     if (a.mode == 0) {
       const uint32_t c = idx & qmask, d = idx >> q;
       addr = base + (d << s) + c;
       sidx = idx;
+      if constexpr (DIST) {
+        const uint32_t col = (cb << q) + c;
+        tw_k = d;
+        tw_col = dd->col_off + col;
+        const uint32_t gaddr = (d << dd->s_glob) + tw_col;
+        if (dd->pull) {
+          src = dd->peer[d >> dd->peer_log];
+          addr = ((d & ((1u << dd->peer_log) - 1)) << dd->s_glob) + tw_col;
+        }
+        Fr v = ld_fr(src + addr);
+        if (dd->tw_on_load) {
+          const uint64_t e = ((uint64_t)tw_col * tw_k) << a.tw_shift;
+          v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
+          v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
+        }
+        if (a.pre_lo) {
+          v = fp_mul(v, ldg_fr(a.pre_lo + (gaddr & ((1u << a.pre_lb) - 1))));
+          v = fp_mul(v, ldg_fr(a.pre_hi + (gaddr >> a.pre_lb)));
+        }
+        st_tile(lo, hi, sidx, v);
+        continue;
+      }
     } else {
       const uint32_t d = idx & rmask, c = idx >> r;
       const uint32_t k1 = (ab << q) + c;
@@ -174,6 +213,26 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(N
     uint32_t addr;
     if (a.mode == 0) {
       const uint32_t col = (cb << q) + c;
+      if constexpr (DIST) {
+        const uint32_t colg = dd->col_off + col;
+        if (!dd->tw_on_load) {
+          const uint64_t e = ((uint64_t)colg * k) << a.tw_shift;
+          v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
+          v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
+        }
+        if (a.post_lo) {
+          const uint32_t gaddr = (k << dd->s_glob) + colg;
+          v = fp_mul(v, ldg_fr(a.post_lo + (gaddr & ((1u << a.post_lb) - 1))));
+          v = fp_mul(v, ldg_fr(a.post_hi + (gaddr >> a.post_lb)));
+        }
+        if (dd->push) {
+          Fr* dst = dd->peer[k >> dd->peer_log];
+          st_fr(dst + (((k & ((1u << dd->peer_log) - 1)) << dd->s_glob) + colg), v);
+        } else {
+          st_fr(out + (base + (k << s) + c), v);
+        }
+        continue;
+      }
       const uint64_t e = ((uint64_t)col * k) << a.tw_shift;
       v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
       if (a.tw_two_level) v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
@@ -188,6 +247,32 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(N
       if (a.scale) v = fp_mul(v, ldg_fr(a.scale));
     }
     st_fr(out + addr, v);
+  }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(NttPassArgs a) {
+  ntt_pass_body<false>(a, nullptr);
+}
+
+// Same pass with global column indexing and (optionally) peer loads / stores: the distributed stage.
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_dist_pass_kernel(NttPassArgs a, NttDistArgs d) {
+  ntt_pass_body<true>(a, &d);
+}
+
+// All-to-all companion for the NCCL path: forward  recv[g][row'][col'] -> out[row'][g][col'],
+// inverse  in[row'][g][col'] -> send[g][row'][col']   (row' < 2^rows_log, g < 2^wl, col' < 2^cols_log).
+__global__ void __launch_bounds__(256) ntt_dist_permute_kernel(const Fr* in, Fr* out, uint32_t rows_log, uint32_t wl,
+                                                               uint32_t cols_log, uint32_t inverse) {
+  const size_t total = (size_t)1 << (rows_log + wl + cols_log);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const size_t c = i & (((size_t)1 << cols_log) - 1);
+    const size_t g = (i >> cols_log) & (((size_t)1 << wl) - 1);
+    const size_t rw = i >> (cols_log + wl);
+    const size_t j = (((g << rows_log) + rw) << cols_log) + c;  // index in the [g][row'][col'] layout
+    if (inverse) st_fr(out + j, ld_fr(in + i));
+    else st_fr(out + i, ld_fr(in + j));
   }
 }
 
@@ -244,6 +329,8 @@ int ntt_init(Ctx* ctx) {
   ZKP_TRY(upload_powers(ctx, &ctx->w_fwd, w, Fr::one(), (size_t)1 << (WLOG - 1)));
   ZKP_TRY(upload_powers(ctx, &ctx->w_inv, fp_inv(w), Fr::one(), (size_t)1 << (WLOG - 1)));
   ZKP_TRY(rt::allow_smem((const void*)ntt_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr)));
+  ZKP_TRY(rt::allow_smem((const void*)ntt_dist_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr)));
+  ZKP_TRY(rt::prefer_smem_carveout((const void*)ntt_dist_pass_kernel));
   return rt::prefer_smem_carveout((const void*)ntt_pass_kernel);  // several 64 KB tiles resident per SM
 }
 
@@ -394,6 +481,113 @@ int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, 
     ZKP_LAUNCH(ntt_pass_kernel, grid, dim3(threads), (size_t)E * sizeof(Fr), ctx->stream, a);
     ctx->ntt_launches++;
   }
+  return rt::check_last();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Distributed four-step transform (one process per GPU; the exchange itself is done by the caller with
+// NCCL, or fused into the stage kernel through peer pointers)
+// ------------------------------------------------------------------------------------------------
+uint32_t ntt_dist_rows_log(uint32_t log_n, uint32_t world_log) {
+  // N = 2^r rows x 2^(log_n - r) columns; every rank needs >= 1 row block and >= 1 column block
+  if (log_n < 2 * world_log || log_n < 2) return 0;
+  uint32_t r = log_n / 2;
+  if (r > RMAX) r = RMAX;
+  if (r < world_log) r = world_log;
+  if (log_n - r < world_log) return 0;
+  return r;
+}
+
+static int get_dist_tables(Ctx* ctx, uint32_t log_n, uint32_t r, bool inverse, NttTables** out) {
+  const uint32_t key = 0x10000u + log_n * 64 + r * 2 + (inverse ? 1 : 0);
+  auto it = ctx->ntt_tables.find(key);
+  if (it != ctx->ntt_tables.end()) {
+    *out = &it->second;
+    return ZKP_OK;
+  }
+  NttTables t;
+  t.log_n = log_n;
+  t.inverse = inverse;
+  t.npass = 1;
+  t.digits[0] = r;
+  t.lb = log_n / 2;
+  Fr w = fr_omega(log_n);
+  if (inverse) w = fp_inv(w);
+  Fr whi = w;
+  for (uint32_t i = 0; i < t.lb; i++) whi = fp_sqr(whi);
+  // inverse: the stage contributes (2^r)^-1; the local transforms of size 2^(log_n - r) carry their own
+  const Fr first = inverse ? fp_inv(fr_from_u64((uint64_t)1 << r)) : Fr::one();
+  ZKP_TRY(upload_powers(ctx, &t.tw_lo, w, first, (size_t)1 << t.lb));
+  ZKP_TRY(upload_powers(ctx, &t.tw_hi, whi, Fr::one(), (size_t)1 << (log_n - t.lb)));
+  auto ins = ctx->ntt_tables.emplace(key, t);
+  *out = &ins.first->second;
+  return ZKP_OK;
+}
+
+int ntt_dist_stage_dev(Ctx* ctx, Fr* data, uint32_t log_n, uint32_t rank, uint32_t world_log, bool inverse,
+                       const Fr* coset_host, Fr* const* peers) {
+  ctx->ntt_launches = 0;
+  const uint32_t r = ntt_dist_rows_log(log_n, world_log);
+  if (r == 0 || log_n > 31 || world_log > 3 || rank >= (1u << world_log)) return ZKP_ERR_INVALID_ARG;
+  NttTables* t = nullptr;
+  ZKP_TRY(get_dist_tables(ctx, log_n, r, inverse, &t));
+  CosetTables* cs = nullptr;
+  if (coset_host) {
+    const Fr one = Fr::one();
+    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, &cs));
+  }
+  const uint32_t s_glob = log_n - r, s_loc = s_glob - world_log;
+  NttPassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = data;
+  a.out = data;
+  a.log_n = log_n;
+  a.r = r;
+  a.s = s_loc;
+  a.q = (TILE_LOG - r < s_loc) ? (TILE_LOG - r) : s_loc;
+  a.mode = 0;
+  a.w = inverse ? ctx->w_inv : ctx->w_fwd;
+  a.tw_lo = t->tw_lo;
+  a.tw_hi = t->tw_hi;
+  a.tw_lb = t->lb;
+  a.tw_shift = 0;
+  a.tw_two_level = 1;
+  a.batch_stride = 0;
+  if (cs && !inverse) { a.pre_lo = cs->lo; a.pre_hi = cs->hi; a.pre_lb = cs->lb; }
+  if (cs && inverse) { a.post_lo = cs->lo; a.post_hi = cs->hi; a.post_lb = cs->lb; }
+  NttDistArgs d;
+  memset(&d, 0, sizeof(d));
+  d.s_glob = s_glob;
+  d.col_off = rank << s_loc;
+  d.tw_on_load = inverse ? 1 : 0;
+  d.peer_log = r - world_log;
+  if (peers) {
+    for (uint32_t g = 0; g < (1u << world_log); g++) {
+      if (!peers[g]) return ZKP_ERR_INVALID_ARG;
+      d.peer[g] = peers[g];
+    }
+    d.push = inverse ? 0 : 1;
+    d.pull = inverse ? 1 : 0;
+  }
+  const uint32_t E = 1u << (r + a.q);
+  const uint32_t tiles = 1u << (s_loc - a.q);
+  uint32_t threads = NTT_THREADS;
+  while (threads > 32 && threads > E / 2) threads >>= 1;
+  ZKP_LAUNCH(ntt_dist_pass_kernel, dim3(tiles, 1, 1), dim3(threads), (size_t)E * sizeof(Fr), ctx->stream, a, d);
+  ctx->ntt_launches = 1;
+  return rt::check_last();
+}
+
+int ntt_dist_permute_dev(Ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, uint32_t world_log, bool inverse) {
+  const uint32_t r = ntt_dist_rows_log(log_n, world_log);
+  if (r == 0 || in == out) return ZKP_ERR_INVALID_ARG;
+  const uint32_t rows_log = r - world_log, cols_log = log_n - r - world_log;
+  const size_t total = (size_t)1 << (log_n - world_log);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  ZKP_LAUNCH(ntt_dist_permute_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, in, out, rows_log, world_log,
+             cols_log, inverse ? 1u : 0u);
   return rt::check_last();
 }
 

@@ -39,10 +39,14 @@ inline int device_count() { return 1; }
 inline int sm_count(int) { return 4; }
 inline int allow_smem(const void*, size_t) { return ZKP_OK; }
 inline int prefer_smem_carveout(const void*) { return ZKP_OK; }
+inline int ipc_export(const void* d, uint8_t h[64]) { memset(h, 0, 64); memcpy(h, &d, sizeof(d)); return ZKP_OK; }  // same process only
+inline int ipc_open(const uint8_t h[64], void** d) { memcpy(d, h, sizeof(*d)); return ZKP_OK; }
+inline int ipc_close(void*) { return ZKP_OK; }
 inline const char* last_error_string() { return "emulator"; }
 }}  // namespace zkp::rt
 #else
 #include <cuda_runtime.h>
+#include <string.h>
 #define ZKP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZKP_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char zkp_dyn_smem_raw[]; \
@@ -73,6 +77,14 @@ inline int allow_smem(const void* fn, size_t bytes) {
 inline int prefer_smem_carveout(const void* fn) {
   return wrap(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+inline int ipc_export(const void* d, uint8_t h[64]) { return wrap(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)h, (void*)d)); }
+inline int ipc_open(const uint8_t h[64], void** d) {
+  cudaIpcMemHandle_t hh;
+  memcpy(&hh, h, 64);
+  return wrap(cudaIpcOpenMemHandle(d, hh, cudaIpcMemLazyEnablePeerAccess));
+}
+inline int ipc_close(void* d) { return d ? wrap(cudaIpcCloseMemHandle(d)) : ZKP_OK; }
 inline const char* last_error_string() { return last_error_slot(); }
 }}  // namespace zkp::rt
 #endif
