@@ -126,6 +126,31 @@ int zkp_ipc_export(zkp_ctx* ctx, const void* dev, uint8_t handle[64]);
 int zkp_ipc_open(zkp_ctx* ctx, const uint8_t handle[64], void** out_dev);
 int zkp_ipc_close(zkp_ctx* ctx, void* dev);
 
+/* ---- device-resident Fr vectors: the O(n) polynomial work the reference's prover does on the CPU between
+ *      its MSMs and FFTs (plonk/src/prover.rs: DensePolynomial add / scale / evaluate / divide), kept in HBM.
+ *      Elements are 32-byte Montgomery Fr; `*_dev` pointers come from zkp_dev_alloc. --------------------- */
+int zkp_dev_upload(zkp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);   /* returns after the copy */
+int zkp_dev_download(zkp_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* returns after the copy */
+int zkp_dev_zero(zkp_ctx* ctx, void* dst_dev, size_t bytes);
+/* out[i] = first * base^i   (`domain.elements()`, coset points, powers of an opening point) */
+int zkp_fr_powers_dev(zkp_ctx* ctx, void* out_dev, const uint64_t base[4], const uint64_t first[4], size_t n);
+/* data[i] = 1 / data[i] (Montgomery's trick; a zero entry poisons its run of 16 -- the reference panics on 1/0) */
+int zkp_fr_batch_inverse_dev(zkp_ctx* ctx, void* data_dev, size_t n);
+/* in-place inclusive scan; op 0 = product, 1 = sum; reverse != 0 scans from the top index down */
+int zkp_fr_scan_dev(zkp_ctx* ctx, void* data_dev, size_t n, int op, int reverse);
+/* out[j] = sum_k coefs[k] * polys[k][j] (j < lens[k])  + c0 at j == 0; count <= 12; out may alias no input */
+int zkp_fr_lincomb_dev(zkp_ctx* ctx, void* out_dev, size_t out_len, uint32_t count, const void* const* polys_dev,
+                       const size_t* lens, const uint64_t* coefs /* count x 4 */, const uint64_t* c0 /* 4 or NULL */);
+/* data[idx[k]] += vals[k], k < count <= 8, applied in order (blinding terms, constant-term edits) */
+int zkp_fr_add_at_dev(zkp_ctx* ctx, void* data_dev, uint32_t count, const size_t* idx, const uint64_t* vals);
+/* out[k] = polys[k](xs[k])  (`Polynomial::evaluate`), count <= 15, one read-back for the whole batch */
+int zkp_fr_eval_dev(zkp_ctx* ctx, uint32_t count, const void* const* polys_dev, const size_t* lens, const uint64_t* xs,
+                    uint64_t* out);
+/* number of coefficients left after DensePolynomial's trailing-zero trim */
+int zkp_fr_trimmed_len_dev(zkp_ctx* ctx, const void* coeffs_dev, size_t n, size_t* out_len);
+/* `KzgScheme::commit_para` (kzg/src/scheme.rs:78-82) for `count` <= 64 scalars at once: scalars[k] * srs[0] */
+int zkp_g1_mul_srs0(zkp_ctx* ctx, const uint64_t* scalars, uint32_t count, uint64_t* out_xy /* count x 12 */);
+
 /* ---- synthetic workloads (bench configs 2/5): n distinct pseudo-random G1 points generated on
  *      the device from a seed (a0 + i*delta) * G, affine, written to bases_dev (n x 96 B). ----- */
 int zkp_g1_generate_bases_dev(zkp_ctx* ctx, uint64_t seed, size_t n, void* bases_dev);

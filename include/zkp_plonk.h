@@ -71,6 +71,41 @@ int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* o
 int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
                     double* timings_ms);
 
+/* Same proof, computed the way prover.rs is written: every `&a * &b` of compute_quotient_polynomial as its own
+ * GPU product (zkp_poly_mul_fr: 2 NTT + pointwise + iNTT at 4n / 8n), polynomials held on the host between
+ * calls.  Kept as an independent cross-check of zkp_plonk_prove (the proofs must be byte-identical). */
+int zkp_plonk_prove_products(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                             double* timings_ms);
+
+/* ---- the two pointwise kernels of the device-resident prover (csrc/poly.cu) -------------------------- */
+/* prover.rs:314-369: num[i], den[i] of the grand-product factor at row i, from the wire / sigma VALUES on the
+ * domain and roots[i] = omega^i. */
+typedef struct zkp_plonk_numden_args {
+  const void *a_dev, *b_dev, *c_dev, *s1_dev, *s2_dev, *s3_dev, *roots_dev;
+  uint64_t beta[4], gamma[4], k1[4], k2[4];
+  size_t n;
+  void *num_dev, *den_dev;
+} zkp_plonk_numden_args;
+int zkp_plonk_numden_dev(zkp_ctx* ctx, const zkp_plonk_numden_args* args);
+
+/* prover.rs:381-444: t = (line1 + line2 - line3 + line4) / Z_H evaluated pointwise on the coset
+ * x_i = h * omega_d^i, d = rho * n (rho = 4, or 8 when 3n + 6 > 4n); every input is the coset evaluation of
+ * the named polynomial, z(omega x_i) is read at index i + rho, zh_inv[i mod rho] = 1 / (x_i^n - 1). */
+typedef struct zkp_plonk_quotient_args {
+  const void *a_dev, *b_dev, *c_dev, *z_dev;
+  const void *ql_dev, *qr_dev, *qo_dev, *qm_dev, *qc_dev, *pi_dev, *s1_dev, *s2_dev, *s3_dev, *l1_dev, *x_dev;
+  uint64_t beta[4], gamma[4], alpha[4], k1[4], k2[4];
+  uint64_t zh_inv[8][4];
+  size_t d;
+  uint32_t rho;
+  void* t_dev;
+} zkp_plonk_quotient_args;
+int zkp_plonk_quotient_dev(zkp_ctx* ctx, const zkp_plonk_quotient_args* args);
+
+/* q_l a + q_r b + q_o c + q_m a b + q_c + pi == 0 on every row (cols: a b c q_l q_r q_o q_m q_c pi VALUES):
+ * what makes prover.rs:404 `expect("No remainder 1")` hold. */
+int zkp_plonk_gate_check_dev(zkp_ctx* ctx, const void* const cols_dev[9], size_t n, int* ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ def _prove_both(zkp, engine, pyref, rc, blinding=BLIND):
     for i in range(3):
         assert cc.poly(f"s_sigma_{i + 1}") == cc_ref.sigma[i]
     proof = zkp.plonk.generate_proof(cc, blinding)
+    # the two native provers (coset-evaluation quotient vs one GPU product per `&a * &b`) agree byte for byte
+    assert zkp.plonk.generate_proof(cc, blinding, products=True).to_bytes() == proof.to_bytes()
     want = ref.generate_proof(cc_ref, srs_pts, blinding)
     return proof, want, cc_ref, srs_pts
 
@@ -76,9 +78,10 @@ def test_wrong_witness_panics(zkp, engine, pyref):
     srs = zkp.Srs.new_from_secret(engine, SECRET, 4)
     zkp.KzgScheme(engine, srs)
     cc = _native_circuit(zkp, rc).compile(engine)
-    with pytest.raises(zkp.plonk.PlonkPanic) as ei:
-        zkp.plonk.generate_proof(cc, BLIND)
-    assert ei.value.status == zkp.plonk.ERR_REMAINDER
+    for products in (False, True):
+        with pytest.raises(zkp.plonk.PlonkPanic) as ei:
+            zkp.plonk.generate_proof(cc, BLIND, products=products)
+        assert ei.value.status == zkp.plonk.ERR_REMAINDER
 
 
 def _chain_circuit(n_gates, seed):
@@ -165,5 +168,35 @@ def test_large_chain_prove_then_verify(zkp, gpu_engine, pyref, log_n):
     assert ref.verify_with_secret(cc_ref, g0, SECRET, p, commit_fn=cm)
     bad = ref.Proof(*proof.commitments(), *(proof.scalars()[:5] + [(proof.bar_z_w + 1) % ref.R]), proof.u, proof.degree)
     assert not ref.verify_with_secret(cc_ref, g0, SECRET, bad, commit_fn=cm)
-    # determinism: same inputs, same bytes
+    # determinism, and agreement with the product-structured prover at a size the oracle cannot reach
     assert zkp.plonk.generate_proof(cc, BLIND).to_bytes() == proof.to_bytes()
+    assert zkp.plonk.generate_proof(cc, BLIND, products=True).to_bytes() == proof.to_bytes()
+
+
+def test_copy_constraint_violation_panics(zkp, engine, pyref):
+    """Every gate satisfied but two wired cells hold different values: the grand product does not close, so
+    line2 - line3 is not divisible by Z_H -- prover.rs:431 expect("No remainder here")."""
+    rc = ref.Circuit()
+    rc.add_multiplication_gate((0, 0, 1), (1, 0, 2), (0, 1, 2), 0)
+    rc.add_multiplication_gate((2, 0, 3), (1, 1, 3), (2, 1, 9), 0)  # a = 3 wired to gate 0's c = 2
+    with pytest.raises(RuntimeError, match="No remainder here"):
+        ref.generate_proof(rc.compile(), pyref.srs_from_secret(SECRET, 2), BLIND)
+    srs = zkp.Srs.new_from_secret(engine, SECRET, 2)
+    zkp.KzgScheme(engine, srs)
+    cc = _native_circuit(zkp, rc).compile(engine)
+    for products in (False, True):
+        with pytest.raises(zkp.plonk.PlonkPanic) as ei:
+            zkp.plonk.generate_proof(cc, BLIND, products=products)
+        assert ei.value.status == zkp.plonk.ERR_REMAINDER
+
+
+def test_srs_too_small(zkp, engine):
+    """scheme.rs:86: the SRS must be longer than the degree n + 2 of z(X)."""
+    rc = ref.circuit_accepted_01()
+    srs = zkp.Srs.new_from_secret(engine, SECRET, 3)  # 6 points < n + 3 = 7
+    zkp.KzgScheme(engine, srs)
+    cc = _native_circuit(zkp, rc).compile(engine)
+    for products in (False, True):
+        with pytest.raises(zkp.plonk.PlonkPanic) as ei:
+            zkp.plonk.generate_proof(cc, BLIND, products=products)
+        assert ei.value.status == 4

@@ -64,6 +64,20 @@ ABI = {
     "zkp_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_ipc_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "zkp_ipc_close": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_dev_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_dev_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_dev_zero": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_fr_powers_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_fr_batch_inverse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_fr_scan_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]),
+    "zkp_fr_lincomb_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_fr_add_at_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_fr_eval_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "zkp_fr_trimmed_len_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.POINTER(ctypes.c_size_t)]),
+    "zkp_g1_mul_srs0": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "zkp_g1_generate_bases_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_bench_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
@@ -280,6 +294,58 @@ class Engine:
     def ipc_close(self, ptr: int) -> None:
         self._check(self.lib.zkp_ipc_close(self._h, ctypes.c_void_p(ptr)))
 
+    # -- device-resident Fr vectors (csrc/poly.cu) -------------------------------------------------
+    def vec(self, data: Optional[np.ndarray] = None, n: Optional[int] = None) -> "DevVec":
+        """Device vector of Fr elements, from an (n, 4) uint64 Montgomery array or zero-filled."""
+        return DevVec(self, data=data, n=n)
+
+    def fr_powers(self, out: "DevVec", base: int, first: int = 1) -> None:
+        b, f = fields.fr_to_mont_array([base]), fields.fr_to_mont_array([first])
+        self._check(self.lib.zkp_fr_powers_dev(self._h, _ptr(out.ptr), _ptr(b), _ptr(f), out.n))
+
+    def fr_batch_inverse(self, v: "DevVec") -> None:
+        self._check(self.lib.zkp_fr_batch_inverse_dev(self._h, _ptr(v.ptr), v.n))
+
+    def fr_scan(self, v: "DevVec", op: str = "mul", reverse: bool = False) -> None:
+        self._check(self.lib.zkp_fr_scan_dev(self._h, _ptr(v.ptr), v.n, 0 if op == "mul" else 1, 1 if reverse else 0))
+
+    def fr_lincomb(self, out: "DevVec", polys: Sequence["DevVec"], coefs: Sequence[int], c0: Optional[int] = None) -> None:
+        k = len(polys)
+        ptrs = (ctypes.c_void_p * k)(*[ctypes.c_void_p(p.ptr) for p in polys])
+        lens = (ctypes.c_size_t * k)(*[p.n for p in polys])
+        cf = fields.fr_to_mont_array(coefs) if k else np.zeros((0, 4), dtype=np.uint64)
+        c0a = None if c0 is None else fields.fr_to_mont_array([c0])
+        self._check(self.lib.zkp_fr_lincomb_dev(self._h, _ptr(out.ptr), out.n, k, ctypes.cast(ptrs, ctypes.c_void_p),
+                                                ctypes.cast(lens, ctypes.c_void_p), _ptr(cf), _ptr(c0a)))
+
+    def fr_add_at(self, v: "DevVec", idx: Sequence[int], vals: Sequence[int]) -> None:
+        k = len(idx)
+        ia = (ctypes.c_size_t * k)(*idx)
+        va = fields.fr_to_mont_array(vals)
+        self._check(self.lib.zkp_fr_add_at_dev(self._h, _ptr(v.ptr), k, ctypes.cast(ia, ctypes.c_void_p), _ptr(va)))
+
+    def fr_eval(self, polys: Sequence["DevVec"], xs: Sequence[int]) -> list:
+        k = len(polys)
+        ptrs = (ctypes.c_void_p * k)(*[ctypes.c_void_p(p.ptr) for p in polys])
+        lens = (ctypes.c_size_t * k)(*[p.n for p in polys])
+        xa = fields.fr_to_mont_array(xs)
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self._check(self.lib.zkp_fr_eval_dev(self._h, k, ctypes.cast(ptrs, ctypes.c_void_p),
+                                             ctypes.cast(lens, ctypes.c_void_p), _ptr(xa), _ptr(out)))
+        return fields.fr_from_mont_array(out)
+
+    def fr_trimmed_len(self, v: "DevVec") -> int:
+        out = ctypes.c_size_t(0)
+        self._check(self.lib.zkp_fr_trimmed_len_dev(self._h, _ptr(v.ptr), v.n, ctypes.byref(out)))
+        return int(out.value)
+
+    def g1_mul_srs0(self, scalars: Sequence[int]) -> list:
+        """`KzgScheme::commit_para` for several scalars at once (kzg/src/scheme.rs:78-82)."""
+        sa = fields.fr_to_mont_array(scalars)
+        out = np.zeros((len(scalars), 12), dtype=np.uint64)
+        self._check(self.lib.zkp_g1_mul_srs0(self._h, _ptr(sa), len(scalars), _ptr(out)))
+        return fields.g1_from_array(out)
+
     # -- synthetic workloads / microbenchmarks ----------------------------------------------------
     def generate_bases_dev(self, seed: int, n: int, bases_dev) -> None:
         self._check(self.lib.zkp_g1_generate_bases_dev(self._h, seed & (2**64 - 1), n, _ptr(bases_dev)))
@@ -288,6 +354,42 @@ class Engine:
         w, l = ctypes.c_double(0), ctypes.c_double(0)
         self._check(self.lib.zkp_bench_imad_peak(self._h, ctypes.byref(w), ctypes.byref(l)))
         return w.value, l.value
+
+
+class DevVec:
+    """n Fr elements (32-byte Montgomery) in device memory owned through zkp_dev_alloc / zkp_dev_free."""
+
+    def __init__(self, engine: Engine, data: Optional[np.ndarray] = None, n: Optional[int] = None):
+        self.eng = engine
+        if data is not None:
+            data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
+            n = data.shape[0]
+        self.n = int(n or 0)
+        self.ptr = engine.dev_alloc(max(self.n, 1) * 32)
+        if data is not None and self.n:
+            engine._check(engine.lib.zkp_dev_upload(engine._h, _ptr(self.ptr), _ptr(data), self.n * 32))
+        elif self.n:
+            engine._check(engine.lib.zkp_dev_zero(engine._h, _ptr(self.ptr), self.n * 32))
+
+    def get(self) -> np.ndarray:
+        out = np.zeros((self.n, 4), dtype=np.uint64)
+        if self.n:
+            self.eng._check(self.eng.lib.zkp_dev_download(self.eng._h, _ptr(out), _ptr(self.ptr), self.n * 32))
+        return out
+
+    def ints(self) -> list:
+        return fields.fr_from_mont_array(self.get())
+
+    def free(self) -> None:
+        if self.ptr and getattr(self.eng, "_h", None):
+            self.eng.dev_free(self.ptr)
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 from . import dist, plonk  # noqa: E402

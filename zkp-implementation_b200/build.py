@@ -16,8 +16,8 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu"]
-HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu", "poly.cu"]
+HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
 HOST_DIR = os.path.join(PKG, "host")
 HOST_SOURCES = ["plonk.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
 HOST_HEADERS = ["mont_host.hpp", "transcript.hpp"]

@@ -5,7 +5,9 @@
 #include <new>
 
 #include "../../include/zkp_b200.h"
+#include "../../include/zkp_plonk.h"
 #include "engine.h"
+#include "poly.h"
 
 using namespace zkp;
 
@@ -381,6 +383,175 @@ int zkp_ipc_close(zkp_ctx* h, void* dev) {
   if (!h) return ZKP_ERR_INVALID_ARG;
   ZKP_TRY(rt::set_device(h->c.device));
   return rt::ipc_close(dev);
+}
+
+// ---- device-resident Fr vectors ------------------------------------------------------------------
+static Fr fr_of(const uint64_t* p) {
+  Fr r;
+  memcpy(r.v, p, 32);
+  return r;
+}
+#define ZKP_ENTER(h)                              \
+  if (!(h)) return ZKP_ERR_INVALID_ARG;           \
+  std::lock_guard<std::mutex> g((h)->c.mu);       \
+  ZKP_TRY(rt::set_device((h)->c.device));         \
+  Ctx* c = &(h)->c
+
+int zkp_dev_upload(zkp_ctx* h, void* dst_dev, const void* src_host, size_t bytes) {
+  ZKP_ENTER(h);
+  if (bytes && (!dst_dev || !src_host)) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::h2d(dst_dev, src_host, bytes, c->stream));
+  return rt::sync(c->stream);
+}
+
+int zkp_dev_download(zkp_ctx* h, void* dst_host, const void* src_dev, size_t bytes) {
+  ZKP_ENTER(h);
+  if (bytes && (!dst_host || !src_dev)) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::d2h(dst_host, src_dev, bytes, c->stream));
+  return rt::sync(c->stream);
+}
+
+int zkp_dev_zero(zkp_ctx* h, void* dst_dev, size_t bytes) {
+  ZKP_ENTER(h);
+  if (bytes && !dst_dev) return ZKP_ERR_INVALID_ARG;
+  return rt::dev_memset(dst_dev, 0, bytes, c->stream);
+}
+
+int zkp_fr_powers_dev(zkp_ctx* h, void* out_dev, const uint64_t base[4], const uint64_t first[4], size_t n) {
+  ZKP_ENTER(h);
+  if (!base || !first || (n && !out_dev)) return ZKP_ERR_INVALID_ARG;
+  return fr_powers_dev(c, (Fr*)out_dev, fr_of(base), fr_of(first), n);
+}
+
+int zkp_fr_batch_inverse_dev(zkp_ctx* h, void* data_dev, size_t n) {
+  ZKP_ENTER(h);
+  if (n && !data_dev) return ZKP_ERR_INVALID_ARG;
+  return fr_batch_inverse_dev(c, (Fr*)data_dev, n);
+}
+
+int zkp_fr_scan_dev(zkp_ctx* h, void* data_dev, size_t n, int op, int reverse) {
+  ZKP_ENTER(h);
+  if ((n && !data_dev) || (op != 0 && op != 1)) return ZKP_ERR_INVALID_ARG;
+  return fr_scan_dev(c, (Fr*)data_dev, n, op, reverse != 0);
+}
+
+int zkp_fr_lincomb_dev(zkp_ctx* h, void* out_dev, size_t out_len, uint32_t count, const void* const* polys_dev,
+                       const size_t* lens, const uint64_t* coefs, const uint64_t* c0) {
+  ZKP_ENTER(h);
+  if ((out_len && !out_dev) || count > LincombArgs::MAX_TERMS || (count && (!polys_dev || !lens || !coefs)))
+    return ZKP_ERR_INVALID_ARG;
+  LincombArgs a;
+  memset(&a, 0, sizeof(a));
+  a.count = count;
+  for (uint32_t k = 0; k < count; k++) {
+    if (lens[k] && !polys_dev[k]) return ZKP_ERR_INVALID_ARG;
+    a.p[k] = (const Fr*)polys_dev[k];
+    a.len[k] = lens[k];
+    a.coef[k] = fr_of(coefs + 4 * k);
+  }
+  if (c0) {
+    a.has_c0 = 1;
+    a.c0 = fr_of(c0);
+  }
+  return fr_lincomb_dev(c, (Fr*)out_dev, out_len, a);
+}
+
+int zkp_fr_add_at_dev(zkp_ctx* h, void* data_dev, uint32_t count, const size_t* idx, const uint64_t* vals) {
+  ZKP_ENTER(h);
+  if (count > SparseAddArgs::MAX_TERMS || (count && (!data_dev || !idx || !vals))) return ZKP_ERR_INVALID_ARG;
+  SparseAddArgs a;
+  memset(&a, 0, sizeof(a));
+  a.count = count;
+  for (uint32_t k = 0; k < count; k++) {
+    a.idx[k] = idx[k];
+    a.val[k] = fr_of(vals + 4 * k);
+  }
+  return fr_add_at_dev(c, (Fr*)data_dev, a);
+}
+
+int zkp_fr_eval_dev(zkp_ctx* h, uint32_t count, const void* const* polys_dev, const size_t* lens, const uint64_t* xs,
+                    uint64_t* out) {
+  ZKP_ENTER(h);
+  if (count >= Ctx::EVAL_SLOTS || (count && (!polys_dev || !lens || !xs || !out))) return ZKP_ERR_INVALID_ARG;
+  for (uint32_t k = 0; k < count; k++) {
+    if (lens[k] && !polys_dev[k]) return ZKP_ERR_INVALID_ARG;
+    ZKP_TRY(fr_eval_queue_dev(c, (const Fr*)polys_dev[k], lens[k], fr_of(xs + 4 * k), k));
+  }
+  return fr_eval_fetch(c, (Fr*)out, count);
+}
+
+int zkp_fr_trimmed_len_dev(zkp_ctx* h, const void* coeffs_dev, size_t n, size_t* out_len) {
+  ZKP_ENTER(h);
+  if (!out_len || (n && !coeffs_dev)) return ZKP_ERR_INVALID_ARG;
+  return fr_trimmed_len_dev(c, (const Fr*)coeffs_dev, n, out_len);
+}
+
+int zkp_g1_mul_srs0(zkp_ctx* h, const uint64_t* scalars, uint32_t count, uint64_t* out_xy) {
+  ZKP_ENTER(h);
+  if (count > 64 || (count && (!scalars || !out_xy))) return ZKP_ERR_INVALID_ARG;
+  if (count && c->srs_len == 0) return ZKP_ERR_SRS_TOO_SMALL;
+  G1Xyzz tmp[64];
+  ZKP_TRY(g1_scalar_mul_dev(c, c->srs, (const Fr*)scalars, count, tmp));
+  for (uint32_t k = 0; k < count; k++) write_affine(tmp[k], out_xy + 12 * k, nullptr);
+  return ZKP_OK;
+}
+
+// ---- PLONK pointwise kernels (include/zkp_plonk.h) ---------------------------------------------------
+int zkp_plonk_numden_dev(zkp_ctx* h, const zkp_plonk_numden_args* a) {
+  ZKP_ENTER(h);
+  if (!a) return ZKP_ERR_INVALID_ARG;
+  PlonkNumDenArgs p;
+  p.a = (const Fr*)a->a_dev; p.b = (const Fr*)a->b_dev; p.c = (const Fr*)a->c_dev;
+  p.s1 = (const Fr*)a->s1_dev; p.s2 = (const Fr*)a->s2_dev; p.s3 = (const Fr*)a->s3_dev;
+  p.roots = (const Fr*)a->roots_dev;
+  p.beta = fr_of(a->beta);
+  p.gamma = fr_of(a->gamma);
+  p.beta_k1 = fp_mul(p.beta, fr_of(a->k1));
+  p.beta_k2 = fp_mul(p.beta, fr_of(a->k2));
+  p.n = a->n;
+  p.num = (Fr*)a->num_dev;
+  p.den = (Fr*)a->den_dev;
+  if (p.n && (!p.a || !p.b || !p.c || !p.s1 || !p.s2 || !p.s3 || !p.roots || !p.num || !p.den)) return ZKP_ERR_INVALID_ARG;
+  return plonk_numden_dev(c, p);
+}
+
+int zkp_plonk_quotient_dev(zkp_ctx* h, const zkp_plonk_quotient_args* a) {
+  ZKP_ENTER(h);
+  if (!a) return ZKP_ERR_INVALID_ARG;
+  PlonkQuotientArgs p;
+  p.a = (const Fr*)a->a_dev; p.b = (const Fr*)a->b_dev; p.c = (const Fr*)a->c_dev; p.z = (const Fr*)a->z_dev;
+  p.ql = (const Fr*)a->ql_dev; p.qr = (const Fr*)a->qr_dev; p.qo = (const Fr*)a->qo_dev; p.qm = (const Fr*)a->qm_dev;
+  p.qc = (const Fr*)a->qc_dev; p.pi = (const Fr*)a->pi_dev;
+  p.s1 = (const Fr*)a->s1_dev; p.s2 = (const Fr*)a->s2_dev; p.s3 = (const Fr*)a->s3_dev;
+  p.l1 = (const Fr*)a->l1_dev; p.x = (const Fr*)a->x_dev;
+  p.beta = fr_of(a->beta);
+  p.gamma = fr_of(a->gamma);
+  p.alpha = fr_of(a->alpha);
+  p.alpha2 = fp_mul(p.alpha, p.alpha);
+  p.beta_k1 = fp_mul(p.beta, fr_of(a->k1));
+  p.beta_k2 = fp_mul(p.beta, fr_of(a->k2));
+  for (int i = 0; i < 8; i++) p.zh_inv[i] = fr_of(a->zh_inv[i]);
+  p.d = a->d;
+  p.rho = a->rho;
+  p.t = (Fr*)a->t_dev;
+  if (p.d && (!p.a || !p.b || !p.c || !p.z || !p.ql || !p.qr || !p.qo || !p.qm || !p.qc || !p.pi || !p.s1 || !p.s2 ||
+              !p.s3 || !p.l1 || !p.x || !p.t))
+    return ZKP_ERR_INVALID_ARG;
+  return plonk_quotient_dev(c, p);
+}
+
+int zkp_plonk_gate_check_dev(zkp_ctx* h, const void* const cols_dev[9], size_t n, int* ok) {
+  ZKP_ENTER(h);
+  if (!cols_dev || !ok) return ZKP_ERR_INVALID_ARG;
+  const Fr* cols[9];
+  for (int i = 0; i < 9; i++) {
+    if (n && !cols_dev[i]) return ZKP_ERR_INVALID_ARG;
+    cols[i] = (const Fr*)cols_dev[i];
+  }
+  bool good = true;
+  ZKP_TRY(plonk_gate_check_dev(c, cols, n, &good));
+  *ok = good ? 1 : 0;
+  return ZKP_OK;
 }
 
 // ---- synthetic workloads / microbenchmarks ------------------------------------------------------

@@ -74,6 +74,11 @@ struct Ctx {
   std::vector<CosetTables> coset_tables;
   DevBuf ntt_scratch, ntt_io, ntt_io2;
 
+  // polynomial layer (poly.cu): scan block totals, queued evaluation results and their partial sums
+  static constexpr uint32_t EVAL_SLOTS = 16;
+  static constexpr uint32_t EVAL_PARTIALS = 4096;  // blocks of 256 x 32 coefficients: up to 2^25 coefficients
+  DevBuf poly_scratch, eval_out, eval_partials;
+
   // MSM state
   MsmScratch msm;
   uint32_t msm_window_bits = 0;  // 0 = choose from n

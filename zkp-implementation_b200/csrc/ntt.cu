@@ -351,6 +351,9 @@ void ntt_destroy(Ctx* ctx) {
   ctx->ntt_scratch.release();
   ctx->ntt_io.release();
   ctx->ntt_io2.release();
+  ctx->poly_scratch.release();
+  ctx->eval_out.release();
+  ctx->eval_partials.release();
 }
 
 static int get_tables(Ctx* ctx, uint32_t log_n, bool inverse, NttTables** out) {

@@ -1,7 +1,16 @@
 // Host orchestration of the reference's PLONK prover over the GPU engine (include/zkp_plonk.h).
 // Round structure and every formula follow plonk/src/prover.rs:61-293 and its helpers; the circuit
-// builder follows plonk/src/circuit.rs and gate.rs.  G1 sums -> zkp_msm_g1, interpolations ->
-// zkp_ntt_fr, polynomial products -> zkp_poly_mul_fr; O(n) scalar work stays on the host (OpenMP).
+// builder follows plonk/src/circuit.rs and gate.rs.  This file is a pure client of the C ABI
+// (include/zkp_b200.h), exactly as the Rust shim would be.
+//
+//   zkp_plonk_prove            device-resident: polynomials live in HBM from compile to the last opening;
+//                              the host only runs the Fiat-Shamir transcript and a few scalar formulas.
+//                              The quotient t(X) is computed from coset evaluations (5 transforms of size
+//                              4n) instead of the reference's 18 polynomial products (54 transforms at
+//                              4n / 8n) -- t is the unique polynomial with t * Z_H = numerator, so its
+//                              coefficients, commitments and everything hashed after them are identical.
+//   zkp_plonk_prove_products   the same proof computed the way prover.rs is written, one GPU polynomial
+//                              product per `&a * &b`, polynomials on the host between calls (cross-check).
 #include "../../include/zkp_plonk.h"
 
 #include <string.h>
@@ -175,6 +184,27 @@ struct zkp_plonk_compiled {
   std::vector<Fr> ev_abc[3];   // wire values on the domain (zero on padding rows)
   std::vector<Fr> ev_sigma[3]; // sigma evaluations on the domain
   Fr k1, k2, omega;
+  // ---- device-resident form (zkp_plonk_prove) ----
+  zkp_ctx* ctx = nullptr;
+  uint32_t rho = 4, log_d = 0;  // quotient coset: d = rho * n points x_i = h * omega_d^i, h = 7
+  size_t d = 0;
+  Fr coset_h;
+  bool gate_ok = true;          // gate equation holds on every row (prover.rs:404)
+  Fr* d_vals = nullptr;         // 12 x n: the columns above as VALUES on the domain
+  Fr* d_coef = nullptr;         // 12 x n: their interpolations, zero padded
+  Fr* d_roots = nullptr;        // n: omega^i
+  Fr* d_cos = nullptr;          // 11 x d: coset evaluations of q_l q_r q_o q_m q_c pi s1 s2 s3 L1, then the points x_i
+  Fr* d_work = nullptr;         // prover workspace (see Work below)
+  size_t work_elems = 0;
+  ~zkp_plonk_compiled() {
+    if (ctx) {
+      zkp_dev_free(ctx, d_vals);
+      zkp_dev_free(ctx, d_coef);
+      zkp_dev_free(ctx, d_roots);
+      zkp_dev_free(ctx, d_cos);
+      zkp_dev_free(ctx, d_work);
+    }
+  }
 };
 
 #define PLONK_TRY(e)                \
@@ -251,12 +281,49 @@ int zkp_plonk_compile(zkp_ctx* ctx, const zkp_plonk_circuit* c, zkp_plonk_compil
     cc->ev_abc[k].assign(cols.begin() + k * n, cols.begin() + (k + 1) * n);
     cc->ev_sigma[k].assign(cols.begin() + (9 + k) * n, cols.begin() + (10 + k) * n);
   }
-  Timers tm;
-  int st = interpolate_batch(ctx, cols, log_n, 12, tm);  // circuit.rs:173-176, 230-232
-  if (st) { delete cc; return st; }
+  // ---- device-resident form: values, interpolations (circuit.rs:173-176, 230-232 as one batched iNTT),
+  //      domain elements, and the coset evaluations of everything the quotient needs that does not depend
+  //      on the blinding / challenges ----
+  cc->ctx = ctx;
+  cc->rho = (n < 8) ? 8 : 4;  // t has 3n + 6 coefficients: needs d >= 3n + 6
+  cc->d = cc->rho * n;
+  cc->log_d = log_n + (cc->rho == 8 ? 3 : 2);
+  cc->coset_h = Fr::from_u64(7);
+  const size_t d = cc->d;
+  int st = 0;
+  auto fail = [&](int code) { delete cc; return code; };
+  if ((st = zkp_dev_alloc(ctx, 12 * n * 32, (void**)&cc->d_vals))) return fail(st);
+  if ((st = zkp_dev_alloc(ctx, 12 * n * 32, (void**)&cc->d_coef))) return fail(st);
+  if ((st = zkp_dev_alloc(ctx, n * 32, (void**)&cc->d_roots))) return fail(st);
+  if ((st = zkp_dev_alloc(ctx, 11 * d * 32, (void**)&cc->d_cos))) return fail(st);
+  if ((st = zkp_dev_upload(ctx, cc->d_vals, cols[0].v, 12 * n * 32))) return fail(st);
+  if ((st = zkp_dev_copy(ctx, cc->d_coef, cc->d_vals, 12 * n * 32))) return fail(st);
+  if ((st = zkp_ntt_fr_dev(ctx, cc->d_coef, log_n, 12, 1, nullptr))) return fail(st);
+  if ((st = zkp_dev_download(ctx, cols[0].v, cc->d_coef, 12 * n * 32))) return fail(st);
   for (int k = 0; k < 12; k++) {
     cc->poly[k].assign(cols.begin() + k * n, cols.begin() + (k + 1) * n);
     trim(cc->poly[k]);
+  }
+  if ((st = zkp_fr_powers_dev(ctx, cc->d_roots, cc->omega.v, one.v, n))) return fail(st);
+  {
+    const void* chk[9];
+    for (int k = 0; k < 9; k++) chk[k] = cc->d_vals + (size_t)k * n;
+    int ok = 1;
+    if ((st = zkp_plonk_gate_check_dev(ctx, chk, n, &ok))) return fail(st);
+    cc->gate_ok = ok != 0;
+  }
+  // coset cache rows: 0..8 = q_l q_r q_o q_m q_c pi s1 s2 s3 (compiled polys 3..11), 9 = L1, 10 = x_i
+  if ((st = zkp_dev_zero(ctx, cc->d_cos, 10 * d * 32))) return fail(st);
+  for (int k = 0; k < 9; k++)
+    if ((st = zkp_dev_copy(ctx, cc->d_cos + (size_t)k * d, cc->d_coef + (size_t)(3 + k) * n, n * 32))) return fail(st);
+  {
+    const Fr n_inv = fr_inv(Fr::from_u64(n));  // l1_poly: interpolation of (1, 0, ..., 0) = (1/n) sum X^i (prover.rs:459-464)
+    if ((st = zkp_fr_powers_dev(ctx, cc->d_cos + 9 * d, one.v, n_inv.v, n))) return fail(st);
+  }
+  if ((st = zkp_ntt_fr_dev(ctx, cc->d_cos, cc->log_d, 10, 0, cc->coset_h.v))) return fail(st);
+  {
+    const Fr eta = fr_omega(cc->log_d);
+    if ((st = zkp_fr_powers_dev(ctx, cc->d_cos + 10 * d, eta.v, cc->coset_h.v, d))) return fail(st);
   }
   *out = cc;
   return 0;
@@ -272,8 +339,8 @@ int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* o
   return 0;
 }
 
-int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
-                    double* timings_ms) {
+int zkp_plonk_prove_products(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                             double* timings_ms) {
   if (!ctx || !cc || !blinding || !out) return ZKP_B200_ERR_INVALID_ARG;
   Timers tm;
   const size_t n = cc->size;
@@ -437,6 +504,262 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* 
   if (!divide_linear(sub_para(z_x, bar_z_w), zeta * w, w_ev_wx).is_zero()) return ZKP_PLONK_ERR_REMAINDER;  // :248-260
   PLONK_TRY(commit(ctx, w_ev_x, cm[7], tm));
   PLONK_TRY(commit(ctx, w_ev_wx, cm[8], tm));
+  ch.feed(cm[7]); ch.feed(cm[8]);
+  Fr u;
+  if (!ch.generate(1, &u)) return ZKP_PLONK_ERR_TRANSCRIPT;
+
+  for (int i = 0; i < 9; i++) memcpy(out->commitments[i], cm[i].xy, 96);
+  for (int i = 0; i < 6; i++) memcpy(out->evaluations[i], bars[i].v, 32);
+  memcpy(out->u, u.v, 32);
+  out->degree = degree;
+  if (timings_ms) {
+    timings_ms[0] = Timers::since(tm.t0);
+    timings_ms[1] = tm.msm;
+    timings_ms[2] = tm.ntt;
+    timings_ms[3] = timings_ms[0] - tm.msm - tm.ntt;
+  }
+  return 0;
+}
+
+// ---- device-resident prover -------------------------------------------------------------------------
+namespace {
+
+struct DevTimers {
+  double msm = 0, ntt = 0;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+};
+
+// Workspace layout inside cc->d_work (element offsets); L = n + 4 slots per coefficient vector.
+struct Work {
+  size_t n, d, L;
+  Fr* base;
+  Fr* coef(int k) const { return base + (size_t)k * L; }           // 0..3 = a, b, c, z coefficients
+  Fr* r() const { return base + 4 * L; }                           // linearisation polynomial
+  Fr* wx() const { return base + 5 * L; }                          // opening numerator / quotient at zeta
+  Fr* wwx() const { return base + 6 * L; }                         // ... at zeta * omega
+  Fr* pw() const { return base + 7 * L; }                          // powers of the opening point
+  Fr* pwi() const { return base + 8 * L; }                         // powers of its inverse
+  Fr* acc() const { return base + 9 * L; }                         // n + 1: grand product
+  Fr* den() const { return base + 10 * L; }                        // n
+  Fr* cos(int k) const { return base + 11 * L + (size_t)k * d; }   // 0..3 = a, b, c, z on the coset
+  Fr* t() const { return base + 11 * L + 4 * d; }                  // d: quotient evaluations -> coefficients
+  static size_t elems(size_t n, size_t d) { return 11 * (n + 4) + 5 * d; }
+};
+
+int dev_commit(zkp_ctx* ctx, const Fr* scalars_dev, size_t len, G1& out, DevTimers& tm) {
+  auto t = std::chrono::steady_clock::now();
+  uint8_t inf = 0;
+  int st = zkp_msm_g1_dev(ctx, scalars_dev, nullptr, len, out.xy, &inf);  // bases = resident SRS
+  tm.msm += Timers::since(t);
+  return st;
+}
+
+// (poly - poly(root)) / (X - root) in place on the device: weight by root^i, suffix sums, unweight.
+// On return the quotient (len - 1 coefficients) starts at data + 1; *rem_zero tells whether the remainder
+// vanished (prover.rs:228-240 / 248-260 assert it).
+int dev_divide_linear(zkp_ctx* ctx, const Work& w, Fr* data, size_t len, const Fr& root, bool* rem_zero) {
+  if (root.is_zero()) return ZKP_B200_ERR_INVALID_ARG;  // probability 2^-255 for a Fiat-Shamir challenge
+  const Fr one = Fr::one(), rinv = fr_inv(root);
+  PLONK_TRY(zkp_fr_powers_dev(ctx, w.pw(), root.v, one.v, len));
+  PLONK_TRY(zkp_fr_powers_dev(ctx, w.pwi(), rinv.v, one.v, len));
+  PLONK_TRY(zkp_fr_mul_pointwise_dev(ctx, data, w.pw(), len));
+  PLONK_TRY(zkp_fr_scan_dev(ctx, data, len, 1, 1));
+  Fr rem;
+  PLONK_TRY(zkp_dev_download(ctx, rem.v, data, 32));
+  *rem_zero = rem.is_zero();
+  return zkp_fr_mul_pointwise_dev(ctx, data, w.pwi(), len);
+}
+
+}  // namespace
+
+int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_t* blinding, zkp_plonk_proof* out,
+                    double* timings_ms) {
+  if (!ctx || !cc_in || !blinding || !out || cc_in->ctx != ctx) return ZKP_B200_ERR_INVALID_ARG;
+  zkp_plonk_compiled* cc = const_cast<zkp_plonk_compiled*>(cc_in);  // the workspace is a cache, not circuit state
+  DevTimers tm;
+  const size_t n = cc->size, d = cc->d;
+  const uint32_t log_n = cc->log_n;
+  const Fr w = cc->omega, one = Fr::one();
+  if (zkp_srs_len(ctx) < n + 3) return ZKP_B200_ERR_SRS_TOO_SMALL;  // scheme.rs:86 for the degree n + 2 commitment
+  if (!cc->d_work) {
+    cc->work_elems = Work::elems(n, d);
+    PLONK_TRY(zkp_dev_alloc(ctx, cc->work_elems * 32, (void**)&cc->d_work));
+  }
+  Work wk{n, d, n + 4, cc->d_work};
+  Fr b[10];
+  for (int i = 1; i <= 9; i++) memcpy(b[i].v, blinding + 4 * (i - 1), 32);
+  G1 cm[9];
+  auto coef_of = [&](int which) { return cc->d_coef + (size_t)which * n; };  // compiled polynomial, n coefficients
+
+  // ---- Round 1 (prover.rs:68-92): a = f_a + (b1 X + b2)(X^n - 1), ... ----
+  PLONK_TRY(zkp_dev_zero(ctx, wk.base, 4 * wk.L * 32));
+  for (int k = 0; k < 3; k++) {
+    PLONK_TRY(zkp_dev_copy(ctx, wk.coef(k), coef_of(k), n * 32));
+    const Fr hi = b[2 * k + 1], lo = b[2 * k + 2];
+    const size_t idx[4] = {0, 1, n, n + 1};
+    const Fr vals[4] = {-lo, -hi, lo, hi};
+    PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.coef(k), 4, idx, vals[0].v));
+    PLONK_TRY(dev_commit(ctx, wk.coef(k), n + 2, cm[k], tm));
+  }
+
+  // ---- Round 2 (prover.rs:98-123, 302-377) ----
+  ChallengeGenerator ch;
+  ch.feed(cm[0]); ch.feed(cm[1]); ch.feed(cm[2]);
+  Fr bg[2];
+  if (!ch.generate(2, bg)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  const Fr beta = bg[0], gamma = bg[1];
+  bool grand_product_ok = true;
+  {
+    zkp_plonk_numden_args a;
+    memset(&a, 0, sizeof(a));
+    a.a_dev = cc->d_vals; a.b_dev = cc->d_vals + n; a.c_dev = cc->d_vals + 2 * n;
+    a.s1_dev = cc->d_vals + 9 * n; a.s2_dev = cc->d_vals + 10 * n; a.s3_dev = cc->d_vals + 11 * n;
+    a.roots_dev = cc->d_roots;
+    memcpy(a.beta, beta.v, 32); memcpy(a.gamma, gamma.v, 32); memcpy(a.k1, cc->k1.v, 32); memcpy(a.k2, cc->k2.v, 32);
+    a.n = n;
+    a.num_dev = wk.acc() + 1;  // acc[0] = 1, acc[i + 1] = acc[i] * num[i] / den[i]
+    a.den_dev = wk.den();
+    PLONK_TRY(zkp_plonk_numden_dev(ctx, &a));
+    PLONK_TRY(zkp_fr_batch_inverse_dev(ctx, wk.den(), n));
+    PLONK_TRY(zkp_fr_mul_pointwise_dev(ctx, wk.acc() + 1, wk.den(), n));
+    PLONK_TRY(zkp_dev_upload(ctx, wk.acc(), one.v, 32));
+    PLONK_TRY(zkp_fr_scan_dev(ctx, wk.acc(), n + 1, 0, 0));
+    // acc[n] is the product over the whole domain: it is 1 exactly when the copy constraints hold, which is
+    // what makes line2 - line3 divisible by Z_H (prover.rs:431 expect("No remainder here"))
+    Fr total;
+    PLONK_TRY(zkp_dev_download(ctx, total.v, wk.acc() + n, 32));
+    grand_product_ok = (total == one);
+    auto t = std::chrono::steady_clock::now();
+    PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.acc(), log_n, 1, 1, nullptr));  // prover.rs:374: acc evaluations -> coefficients
+    tm.ntt += Timers::since(t);
+    PLONK_TRY(zkp_dev_copy(ctx, wk.coef(3), wk.acc(), n * 32));
+    const size_t idx[6] = {0, 1, 2, n, n + 1, n + 2};  // + (b7 X^2 + b8 X + b9)(X^n - 1)
+    const Fr vals[6] = {-b[9], -b[8], -b[7], b[9], b[8], b[7]};
+    PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.coef(3), 6, idx, vals[0].v));
+  }
+  PLONK_TRY(dev_commit(ctx, wk.coef(3), n + 3, cm[3], tm));
+
+  // ---- Round 3 (prover.rs:136-150, 381-444) ----
+  ch.feed(cm[3]);
+  Fr alpha;
+  if (!ch.generate(1, &alpha)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  if (!cc->gate_ok) return ZKP_PLONK_ERR_REMAINDER;       // "No remainder 1"
+  if (!grand_product_ok) return ZKP_PLONK_ERR_REMAINDER;  // "No remainder here" (line 2 - line 3)
+  {
+    PLONK_TRY(zkp_dev_zero(ctx, wk.cos(0), 4 * d * 32));
+    for (int k = 0; k < 4; k++) PLONK_TRY(zkp_dev_copy(ctx, wk.cos(k), wk.coef(k), (n + 3) * 32));
+    auto t = std::chrono::steady_clock::now();
+    PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.cos(0), cc->log_d, 4, 0, cc->coset_h.v));
+    tm.ntt += Timers::since(t);
+    zkp_plonk_quotient_args q;
+    memset(&q, 0, sizeof(q));
+    q.a_dev = wk.cos(0); q.b_dev = wk.cos(1); q.c_dev = wk.cos(2); q.z_dev = wk.cos(3);
+    const Fr* cs = cc->d_cos;
+    q.ql_dev = cs; q.qr_dev = cs + d; q.qo_dev = cs + 2 * d; q.qm_dev = cs + 3 * d; q.qc_dev = cs + 4 * d;
+    q.pi_dev = cs + 5 * d; q.s1_dev = cs + 6 * d; q.s2_dev = cs + 7 * d; q.s3_dev = cs + 8 * d;
+    q.l1_dev = cs + 9 * d; q.x_dev = cs + 10 * d;
+    memcpy(q.beta, beta.v, 32); memcpy(q.gamma, gamma.v, 32); memcpy(q.alpha, alpha.v, 32);
+    memcpy(q.k1, cc->k1.v, 32); memcpy(q.k2, cc->k2.v, 32);
+    // Z_H(x_i) = h^n (omega_d^n)^i - 1 with omega_d^n a primitive rho-th root of unity
+    const Fr hn = fr_pow(cc->coset_h, n), wr = fr_omega(cc->rho == 8 ? 3 : 2);
+    Fr cur = hn;
+    for (uint32_t i = 0; i < cc->rho; i++) {
+      const Fr zi = fr_inv(cur - one);
+      memcpy(q.zh_inv[i], zi.v, 32);
+      cur = cur * wr;
+    }
+    q.d = d;
+    q.rho = cc->rho;
+    q.t_dev = wk.t();
+    PLONK_TRY(zkp_plonk_quotient_dev(ctx, &q));
+    t = std::chrono::steady_clock::now();
+    PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.t(), cc->log_d, 1, 1, cc->coset_h.v));
+    tm.ntt += Timers::since(t);
+  }
+  // SlicePoly::new (slice_polynomial.rs:22-43) on the trimmed quotient
+  size_t t_len = 0;
+  PLONK_TRY(zkp_fr_trimmed_len_dev(ctx, wk.t(), d, &t_len));
+  size_t tmp = t_len / 3;
+  if (tmp * 3 < t_len) tmp++;
+  if (tmp == 0) return ZKP_B200_ERR_EMPTY_POLY;  // `chunks(0)` panics in the reference
+  size_t slice_len[3];
+  for (int i = 0; i < 3; i++) {
+    const size_t lo = std::min(t_len, (size_t)i * tmp), hi = std::min(t_len, (size_t)(i + 1) * tmp);
+    slice_len[i] = hi - lo;
+    PLONK_TRY(dev_commit(ctx, wk.t() + lo, slice_len[i], cm[4 + i], tm));
+  }
+  const uint64_t degree = (uint64_t)tmp - 1;
+
+  // ---- Round 4 (prover.rs:156-178) ----
+  ch.feed(cm[4]); ch.feed(cm[5]); ch.feed(cm[6]);
+  Fr zeta;
+  if (!ch.generate(1, &zeta)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  const Fr zeta_w = zeta * w;
+  Fr ev[7];
+  {
+    const void* polys[7] = {wk.coef(0), wk.coef(1), wk.coef(2), coef_of(9), coef_of(10), wk.coef(3), coef_of(8)};
+    const size_t lens[7] = {n + 2, n + 2, n + 2, n, n, n + 3, n};
+    Fr xs[7] = {zeta, zeta, zeta, zeta, zeta, zeta_w, zeta};
+    PLONK_TRY(zkp_fr_eval_dev(ctx, 7, polys, lens, xs[0].v, ev[0].v));
+  }
+  const Fr bar_a = ev[0], bar_b = ev[1], bar_c = ev[2], bar_s1 = ev[3], bar_s2 = ev[4], bar_z_w = ev[5], pi_e = ev[6];
+
+  // ---- Round 5 (prover.rs:183-272) ----
+  const Fr bars[6] = {bar_a, bar_b, bar_c, bar_s1, bar_s2, bar_z_w};
+  {
+    G1 para[6];
+    auto t = std::chrono::steady_clock::now();
+    PLONK_TRY(zkp_g1_mul_srs0(ctx, bars[0].v, 6, para[0].xy));  // scheme.commit_para x 6
+    tm.msm += Timers::since(t);
+    for (int i = 0; i < 6; i++) ch.feed(para[i]);
+  }
+  Fr v;
+  if (!ch.generate(1, &v)) return ZKP_PLONK_ERR_TRANSCRIPT;
+  // compute_linearisation_polynomial (prover.rs:469-568) as one linear combination of resident vectors
+  const Fr alpha2 = alpha * alpha;
+  const Fr sc2 = (bar_a + beta * zeta + gamma) * (bar_b + beta * cc->k1 * zeta + gamma) * (bar_c + beta * cc->k2 * zeta + gamma) * alpha;
+  const Fr sc3 = (bar_a + beta * bar_s1 + gamma) * (bar_b + beta * bar_s2 + gamma) * bar_z_w * alpha;
+  const Fr z_h_e = fr_pow(zeta, n) - one;
+  // l1_poly(domain).evaluate(zeta) = (1/n) sum zeta^i = (zeta^n - 1) / (n (zeta - 1))
+  const Fr l1_e = (zeta == one) ? one : z_h_e * fr_inv(Fr::from_u64(n) * (zeta - one));
+  const Fr zm = fr_pow(zeta, degree + 1);
+  const size_t r_len = std::max(n + 3, tmp);
+  {
+    const void* polys[10] = {coef_of(6), coef_of(3), coef_of(4), coef_of(5), coef_of(7), wk.coef(3), coef_of(11),
+                             wk.t(), wk.t() + std::min(t_len, tmp), wk.t() + std::min(t_len, 2 * tmp)};
+    const size_t lens[10] = {n, n, n, n, n, n + 3, n, slice_len[0], slice_len[1], slice_len[2]};
+    const Fr coefs[10] = {bar_a * bar_b, bar_a, bar_b, bar_c, one, sc2 + l1_e * alpha2, -(beta * sc3),
+                          -z_h_e, -(z_h_e * zm), -(z_h_e * zm * zm)};
+    const Fr c0 = pi_e - (bar_c + gamma) * sc3 - l1_e * alpha2;
+    PLONK_TRY(zkp_fr_lincomb_dev(ctx, wk.r(), r_len, 10, polys, lens, coefs[0].v, c0.v));
+  }
+  Fr bar_r;
+  {
+    const void* polys[1] = {wk.r()};
+    const size_t lens[1] = {r_len};
+    PLONK_TRY(zkp_fr_eval_dev(ctx, 1, polys, lens, zeta.v, bar_r.v));
+  }
+  const Fr v2 = v * v, v3 = v2 * v, v4 = v3 * v, v5 = v4 * v;
+  bool rem_ok = false;
+  {
+    const void* polys[6] = {wk.r(), wk.coef(0), wk.coef(1), wk.coef(2), coef_of(9), coef_of(10)};
+    const size_t lens[6] = {r_len, n + 2, n + 2, n + 2, n, n};
+    const Fr coefs[6] = {one, v, v2, v3, v4, v5};
+    const Fr c0 = -(bar_r + v * bar_a + v2 * bar_b + v3 * bar_c + v4 * bar_s1 + v5 * bar_s2);
+    PLONK_TRY(zkp_fr_lincomb_dev(ctx, wk.wx(), r_len, 6, polys, lens, coefs[0].v, c0.v));
+    PLONK_TRY(dev_divide_linear(ctx, wk, wk.wx(), r_len, zeta, &rem_ok));
+    if (!rem_ok) return ZKP_PLONK_ERR_REMAINDER;  // "w_ev_x was computed incorrectly"
+    PLONK_TRY(dev_commit(ctx, wk.wx() + 1, r_len - 1, cm[7], tm));
+  }
+  {
+    PLONK_TRY(zkp_dev_copy(ctx, wk.wwx(), wk.coef(3), (n + 3) * 32));
+    const size_t idx[1] = {0};
+    const Fr vals[1] = {-bar_z_w};
+    PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.wwx(), 1, idx, vals[0].v));
+    PLONK_TRY(dev_divide_linear(ctx, wk, wk.wwx(), n + 3, zeta_w, &rem_ok));
+    if (!rem_ok) return ZKP_PLONK_ERR_REMAINDER;  // "w_ev_wx was computed incorrectly"
+    PLONK_TRY(dev_commit(ctx, wk.wwx() + 1, n + 2, cm[8], tm));
+  }
   ch.feed(cm[7]); ch.feed(cm[8]);
   Fr u;
   if (!ch.generate(1, &u)) return ZKP_PLONK_ERR_TRANSCRIPT;
