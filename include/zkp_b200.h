@@ -68,6 +68,12 @@ int zkp_srs_upload(zkp_ctx* ctx, const uint64_t* xy /* n x 12 */, const uint8_t*
 /* Adopt `n` affine points already in device memory (copied device-to-device). */
 int zkp_srs_upload_dev(zkp_ctx* ctx, const void* xy_dev, size_t n);
 size_t zkp_srs_len(const zkp_ctx* ctx);
+/* Fixed-base table over the resident SRS (called once next to `KzgScheme::new`): for every window w of the
+ * signed-digit recoding the table holds 2^(c w) * srs[i], so all windows of an MSM share one bucket set.
+ * window_bits = 0 picks c from the SRS length.  Costs (255 / c + 1) x the SRS in HBM (16.5 GiB at 2^24, c = 24)
+ * and one pass of c doublings per entry; zkp_msm_g1 / zkp_msm_g1_dev with the SRS then use it automatically.
+ * Uploading or generating a new SRS drops the table. */
+int zkp_srs_precompute(zkp_ctx* ctx, uint32_t window_bits);
 /* `Srs::new_from_secret` (kzg/src/srs.rs:48-69): fill the resident SRS with [secret^i * G], i < n,
  * computed on the GPU; optionally copy the points back to `xy_out` (n x 12 u64, may be NULL). */
 int zkp_srs_generate(zkp_ctx* ctx, const uint64_t secret[4], size_t n, uint64_t* xy_out);

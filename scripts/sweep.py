@@ -50,6 +50,25 @@ def main():
             print(json.dumps({"op": "msm", "log_n": log_n, "ms": ms, "wall_ms": wall, "c": c, "windows": w,
                               "phases_ms": eng.last_phase_ms(), "launches": eng.last_launches("msm"),
                               "mpoints_per_s": n / ms / 1e3}), flush=True)
+        # fixed-base path: the same points as a resident SRS with the precomputed window table
+        for log_n in (16, 18, 20, 22, 24):
+            n = 1 << log_n
+            eng.srs_upload_dev(bases, n)
+            for bits in ((0,) if log_n < 24 else (0, 22, 23)):
+                t0 = time.perf_counter()
+                eng.srs_precompute(bits)
+                torch.cuda.synchronize()
+                t_tab = time.perf_counter() - t0
+                steps = 10 if log_n <= 20 else 4
+                ms = timed(lambda: eng.msm_dev(scalars, None, n), steps)
+                c, w = eng.last_msm_shape()
+                ref = eng.msm_dev(scalars, bases, n)[0]
+                same = bool((eng.msm_dev(scalars, None, n)[0] == ref).all())
+                print(json.dumps({"op": "msm_fixed_base", "log_n": log_n, "ms": ms, "c": c, "windows": w,
+                                  "table_build_s": t_tab, "table_gib": w * n * 96 / 2**30, "matches_windowed": same,
+                                  "phases_ms": eng.last_phase_ms(), "launches": eng.last_launches("msm"),
+                                  "mpoints_per_s": n / ms / 1e3}), flush=True)
+        eng.srs_upload_dev(bases, 1)
         del bases, scalars
         torch.cuda.empty_cache()
     if what in ("all", "ntt"):

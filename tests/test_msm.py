@@ -96,3 +96,42 @@ def test_fold_partials(zkp, engine, coracle):
         parts.append(rec)
     out, inf = engine.fold_partials(np.stack(parts))
     assert (out == whole).all() and not inf
+
+
+@pytest.mark.parametrize("bits", [0, 3, 9, 14])
+def test_fixed_base_table(zkp, engine, coracle, pyref, bits):
+    """zkp_srs_precompute: every window of the signed-digit recoding reads its own 2^(c w)-shifted copy of the
+    SRS and all windows share one bucket set.  Same sums as the windowed path / the oracle, for the whole SRS,
+    a prefix (>= len/4 uses the table, shorter prefixes fall back to the windowed path), corner-case scalars
+    and an SRS containing the point at infinity."""
+    F = zkp.fields
+    n = 600
+    b = coracle.srs(F.fr_to_mont_array([0x5151]), n)
+    b[17] = 0  # infinity base: its shifted copies must stay at infinity
+    s = F.random_fr_mont(61, n)
+    s[3] = 0
+    s[4] = F.fr_to_mont_array([1])[0]
+    s[5] = F.fr_to_mont_array([pyref.R - 1])[0]
+    engine.srs_upload(b)
+    engine.srs_precompute(bits)
+    try:
+        for m in (n, 599, 300, 150, 149, 7, 1):
+            out, inf = engine.msm(s[:m])
+            assert (out == coracle.msm_pippenger(s[:m], b[:m])).all() and not inf, m
+        zero = np.zeros((n, 4), dtype=np.uint64)
+        assert engine.msm(zero)[1]
+        rm1 = F.fr_to_mont_array([pyref.R - 1] * n)
+        assert (engine.msm(rm1)[0] == coracle.msm_pippenger(rm1, b)).all()
+    finally:
+        engine.srs_upload(b[:1])  # drops the table
+
+
+def test_precompute_then_new_srs_drops_table(zkp, engine, coracle):
+    F = zkp.fields
+    b1 = coracle.srs(F.fr_to_mont_array([21]), 64)
+    b2 = coracle.srs(F.fr_to_mont_array([22]), 64)
+    s = F.random_fr_mont(71, 64)
+    engine.srs_upload(b1)
+    engine.srs_precompute(5)
+    engine.srs_upload(b2)  # a stale table would give sums over b1
+    assert (engine.msm(s)[0] == coracle.msm_pippenger(s, b2)).all()

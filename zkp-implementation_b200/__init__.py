@@ -37,6 +37,7 @@ ABI = {
     "zkp_srs_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zkp_srs_upload_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zkp_srs_len": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "zkp_srs_precompute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
     "zkp_srs_generate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_msm_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_msm_g1_bases": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -180,6 +181,10 @@ class Engine:
 
     def srs_upload_dev(self, bases_dev, n: int) -> None:
         self._check(self.lib.zkp_srs_upload_dev(self._h, _ptr(bases_dev), n))
+
+    def srs_precompute(self, window_bits: int = 0) -> None:
+        """Build the fixed-base table over the resident SRS (one bucket set for all windows)."""
+        self._check(self.lib.zkp_srs_precompute(self._h, window_bits))
 
     def srs_len(self) -> int:
         return int(self.lib.zkp_srs_len(self._h))

@@ -76,6 +76,7 @@ void zkp_ctx_destroy(zkp_ctx* h) {
   ntt_destroy(&h->c);
   msm_destroy(&h->c);
   rt::dev_free(h->c.srs);
+  rt::dev_free(h->c.srs_tab);
 #ifndef ZKP_EMU
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
 #endif
@@ -134,7 +135,10 @@ static int stage_affine(Ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n
 
 static int srs_alloc(Ctx* c, size_t n) {
   rt::dev_free(c->srs);
+  rt::dev_free(c->srs_tab);
   c->srs = nullptr;
+  c->srs_tab = nullptr;
+  c->srs_tab_c = 0;
   c->srs_len = 0;
   ZKP_TRY(rt::dev_malloc((void**)&c->srs, n * sizeof(G1Affine)));
   c->srs_len = n;
@@ -161,6 +165,13 @@ int zkp_srs_upload_dev(zkp_ctx* h, const void* xy_dev, size_t n) {
 
 size_t zkp_srs_len(const zkp_ctx* h) { return h ? h->c.srs_len : 0; }
 
+int zkp_srs_precompute(zkp_ctx* h, uint32_t window_bits) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return msm_precompute_dev(&h->c, window_bits);
+}
+
 int zkp_srs_generate(zkp_ctx* h, const uint64_t secret[4], size_t n, uint64_t* xy_out) {
   if (!h || !secret) return ZKP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(h->c.mu);
@@ -178,6 +189,9 @@ static int msm_nolock(Ctx* c, const void* scalars_dev, const void* bases_dev, si
   const G1Affine* bases = (const G1Affine*)bases_dev;
   if (!bases) {
     if (n > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
+    // fixed-base table: its window width was tuned for the whole SRS, so short prefixes stay windowed
+    if (c->srs_tab && n >= c->srs_len / 4)
+      return msm_run_dev(c, (const Fr*)scalars_dev, c->srs_tab, n, acc, c->srs_tab_c, c->srs_len);
     bases = c->srs;
   }
   return msm_run_dev(c, (const Fr*)scalars_dev, bases, n, acc);

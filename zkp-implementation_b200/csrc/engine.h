@@ -66,6 +66,9 @@ struct Ctx {
   // SRS bases resident on the device (kzg/src/srs.rs:14-21 `g1_points`)
   G1Affine* srs = nullptr;
   size_t srs_len = 0;
+  // fixed-base table over the SRS (zkp_srs_precompute): window w = 2^(c w) * srs[i], w < srs_tab_windows
+  G1Affine* srs_tab = nullptr;
+  uint32_t srs_tab_c = 0, srs_tab_windows = 0;
 
   // NTT state
   Fr* w_fwd = nullptr;  // omega_{2^WLOG}^i, i < 2^(WLOG-1)
@@ -108,7 +111,10 @@ int ntt_dist_permute_dev(Ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, uint32
 // ---- MSM (msm.cu) ----
 // result: W window sums are reduced on the device; the final Horner over windows and the single
 // Fq inversion run on the host (272 group operations out of ~n*W).
-int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size_t n, G1Xyzz* out_host);
+// fixed_c != 0: `bases_dev` is a fixed-base table built for window width fixed_c (windows table_stride apart)
+int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size_t n, G1Xyzz* out_host,
+                uint32_t fixed_c = 0, size_t table_stride = 0);
+int msm_precompute_dev(Ctx* ctx, uint32_t window_bits);
 void msm_destroy(Ctx* ctx);
 
 }  // namespace zkp

@@ -85,7 +85,9 @@ static uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-static int normalise(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) {
+int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out);
+static int normalise(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) { return normalise_dev(ctx, tmp, n, out); }
+int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) {
   const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
   ZKP_LAUNCH(batch_normalise_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
              ctx->stream, tmp, n, out);

@@ -6,18 +6,23 @@
 // normalised affine representative, so the result is bit-identical to the reference's per-term
 // double-and-add no matter how the sum is scheduled.
 //
-// Pipeline (all on one stream, no host synchronisation until the W window sums come back):
+// Pipeline (all on one stream):
 //   1. recode      scalars: Montgomery -> canonical -> W signed c-bit digits; one (bucket, point|sign)
-//                  pair per digit, laid out window-major
-//   2. sort        per window radix sort of the pairs by bucket (cub::DeviceRadixSort)
+//                  pair per digit
+//   2. sort        ONE radix sort of all n*W pairs by global bucket id (cub::DeviceRadixSort)
 //   3. boundaries  start/end of every bucket's run in the sorted order
 //   4. tasks       buckets longer than S_max are split so no thread owns an unbounded run; the task
 //                  list is sorted by run length (longest first) so the 32 lanes of a warp finish together
 //   5. accumulate  one thread per task: XYZZ accumulator += affine base (mixed add, 8M+2S),
 //                  next base prefetched while the current add runs
-//   6. reduce      per window: running-sum trick over segments of the bucket array, then a tree
-//   7. host        Horner over the W window sums (c doublings + 1 add each) -- ~270 group
-//                  operations out of ~n*W -- and the caller normalises with one Fq inversion
+//   6. reduce      sum_b (b+1) B_b per bucket set as a base-16 digit recursion: every level is a batch of
+//                  independent 16-element running sums, so even a few thousand buckets fill the GPU
+//   7. host        windowed mode only: Horner over the W window sums; the caller normalises (one inversion)
+//
+// Two modes.  WINDOWED (ad-hoc bases): window w has its own 2^(c-1) buckets.  FIXED-BASE (the resident SRS
+// after zkp_srs_precompute): the table holds 2^(c w) P_i for every window, so digit w of scalar i selects
+// table entry (w, i) and ALL windows share one bucket set -- W times fewer buckets to reduce, no Horner, and
+// the cheaper reduction lets c grow by a few bits (fewer windows, fewer additions).
 #include <string.h>
 
 #include "engine.h"
@@ -34,7 +39,6 @@ namespace zkp {
 
 static constexpr uint32_t ACC_THREADS = 128;
 static constexpr uint32_t RED_THREADS = 128;
-static constexpr uint32_t SEG_LOG = 5;       // buckets per reduce thread = 32
 static constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmTask {
@@ -43,11 +47,12 @@ struct MsmTask {
 };
 
 // ---- 1. recode ---------------------------------------------------------------------------------
-// keys[w*n + i] = |digit| - 1 (bucket index, weight |digit|) or nbuckets for a zero digit
-// vals[w*n + i] = i | sign << 31
+// keys[w*n + i] = global bucket id of digit w of scalar i (weight |digit| = id within the set + 1), or the
+//                 sentinel `total_buckets` for a zero digit
+// vals[w*n + i] = base index | sign << 31; fixed-base mode: index (w * table_stride + i) into the table
 __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ scalars, uint32_t n, uint32_t c,
-                                                         uint32_t nwin, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals) {
+                                                         uint32_t nwin, uint32_t table_stride, uint32_t fixed,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + i);
@@ -57,6 +62,7 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ 
   s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
   s = fp_from_mont(s);  // `cof.into_bigint()` inside ark-ec's scalar mul (scheme.rs:92)
   const uint32_t nbuckets = 1u << (c - 1);
+  const uint32_t sentinel = fixed ? nbuckets : nbuckets * nwin;
   const uint32_t cmask = (1u << c) - 1;
   uint32_t carry = 0;
   for (uint32_t w = 0; w < nwin; w++) {
@@ -78,26 +84,22 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ 
       carry = 0;
     }
     const size_t o = (size_t)w * n + i;
-    keys[o] = d ? (d - 1) : nbuckets;
-    vals[o] = i | (neg && d ? SIGN_BIT : 0u);
+    keys[o] = d ? ((fixed ? 0u : w * nbuckets) + d - 1) : sentinel;
+    vals[o] = ((fixed ? w * table_stride : 0u) + i) | (neg && d ? SIGN_BIT : 0u);
   }
 }
 
 // ---- 3. bucket boundaries ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_bounds_kernel(const uint32_t* __restrict__ skeys, uint32_t n, uint32_t nwin,
-                                                         uint32_t nbuckets, uint32_t* __restrict__ bstart,
+__global__ void __launch_bounds__(256) msm_bounds_kernel(const uint32_t* __restrict__ skeys, size_t total,
+                                                         uint32_t total_buckets, uint32_t* __restrict__ bstart,
                                                          uint32_t* __restrict__ bend) {
-  const size_t total = (size_t)n * nwin;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; idx < total; idx += stride) {
-    const uint32_t w = (uint32_t)(idx / n);
-    const uint32_t i = (uint32_t)(idx - (size_t)w * n);
     const uint32_t key = skeys[idx];
-    if (key >= nbuckets) continue;
-    const size_t gb = (size_t)w * nbuckets + key;
-    if (i == 0 || skeys[idx - 1] != key) bstart[gb] = (uint32_t)idx;
-    if (i == n - 1 || skeys[idx + 1] != key) bend[gb] = (uint32_t)idx + 1;
+    if (key >= total_buckets) continue;
+    if (idx == 0 || skeys[idx - 1] != key) bstart[key] = (uint32_t)idx;
+    if (idx == total - 1 || skeys[idx + 1] != key) bend[key] = (uint32_t)idx + 1;
   }
 }
 
@@ -160,43 +162,60 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTa
 }
 
 // ---- 6. reduce -----------------------------------------------------------------------------------
-// One thread per segment of 2^SEG_LOG consecutive buckets of one window:
-//   seg_out = sum_{b in segment} (b + 1) * bucket[b]
-__global__ void __launch_bounds__(RED_THREADS) msm_segment_reduce_kernel(const G1Xyzz* __restrict__ partials,
-                                                                         const uint32_t* __restrict__ task_off,
-                                                                         const uint32_t* __restrict__ ntask,
-                                                                         uint32_t nbuckets, uint32_t nwin, uint32_t seg_log,
-                                                                         G1Xyzz* __restrict__ seg_out) {
-  const uint32_t nseg = nbuckets >> seg_log;  // per window
+// F = sum_b (b + 1) B_b over one bucket set.  Write b in base L = 2^RED_LOG: b + 1 = 1 + sum_l d_l(b) L^l, so
+//   F = G + sum_l L^l A_l,   G = sum_b B_b,   A_l = sum_b d_l(b) B_b.
+// Level l works on the array X^l (X^0 = buckets, X^(l+1)[g] = sum of the L elements of group g of X^l): one
+// thread per group does a running sum, producing S[g] = X^(l+1)[g] and T[g] = sum_j j X^l[gL + j]; A_l is the
+// sum of T over the groups (xyzz_sum_kernel).  The last level has one group, whose S is G.
+static constexpr uint32_t RED_LOG = 4;
+static constexpr uint32_t RED_L = 1u << RED_LOG;
+static constexpr uint32_t MAX_RED_LEVELS = 8;
+
+// in_mode 0: element b of bucket set w is the sum of the partials of global bucket w*m + b (tasks of a split
+// bucket); in_mode 1: element = in[w*m + b].
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1Xyzz* __restrict__ in,
+                                                                       const uint32_t* __restrict__ task_off,
+                                                                       const uint32_t* __restrict__ ntask, uint32_t in_mode,
+                                                                       uint32_t m, uint32_t nsets, G1Xyzz* __restrict__ s_out,
+                                                                       G1Xyzz* __restrict__ t_out) {
+  const uint32_t groups = (m + RED_L - 1) >> RED_LOG;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nseg * nwin) return;
-  const uint32_t w = t / nseg, seg = t - w * nseg;
-  const uint32_t lo = seg << seg_log;
+  if (t >= groups * nsets) return;
+  const uint32_t w = t / groups, g = t - w * groups;
+  const uint32_t lo = g << RED_LOG;
   G1Xyzz run = G1Xyzz::infinity(), tot = G1Xyzz::infinity();
-  for (int j = (1 << seg_log) - 1; j >= 0; j--) {
-    const uint32_t gb = w * nbuckets + lo + (uint32_t)j;
-    const uint32_t nt = ntask[gb], off = task_off[gb];
-    for (uint32_t k = 0; k < nt; k++) {
-      G1Xyzz p = ld_xyzz(partials + off + k);
-      xyzz_add(run, p);
+  for (int j = (int)RED_L - 1; j >= 0; j--) {
+    const uint32_t b = lo + (uint32_t)j;
+    if (b < m) {
+      const size_t gb = (size_t)w * m + b;
+      if (in_mode == 0) {
+        const uint32_t nt = ntask[gb], off = task_off[gb];
+        for (uint32_t k = 0; k < nt; k++) {
+          G1Xyzz p = ld_xyzz(in + off + k);
+          xyzz_add(run, p);
+        }
+      } else {
+        G1Xyzz p = ld_xyzz(in + gb);
+        xyzz_add(run, p);
+      }
     }
-    xyzz_add(tot, run);
+    if (j > 0) xyzz_add(tot, run);  // element j ends up counted j times
   }
-  if (lo) {
-    G1Xyzz shifted = xyzz_mul_u32(run, lo);
-    xyzz_add(tot, shifted);
-  }
-  st_xyzz(seg_out + t, tot);
+  st_xyzz(s_out + t, run);
+  st_xyzz(t_out + t, tot);
 }
 
-// One block per window: sum the window's segment results.
-__global__ void __launch_bounds__(RED_THREADS) msm_window_reduce_kernel(const G1Xyzz* __restrict__ seg_out, uint32_t nseg,
-                                                                        G1Xyzz* __restrict__ win_out) {
+// out[w * out_stride + bx] = sum of in[w * in_stride + bx * chunk ... + chunk) (clipped to count)
+__global__ void __launch_bounds__(RED_THREADS) xyzz_sum_kernel(const G1Xyzz* __restrict__ in, uint32_t count,
+                                                               uint32_t in_stride, uint32_t chunk, G1Xyzz* __restrict__ out,
+                                                               uint32_t out_stride) {
   __shared__ G1Xyzz sh[RED_THREADS];
-  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  const uint32_t w = blockIdx.y, tid = threadIdx.x;
+  const uint32_t lo = blockIdx.x * chunk;
+  const uint32_t hi = (lo + chunk < count) ? lo + chunk : count;
   G1Xyzz acc = G1Xyzz::infinity();
-  for (uint32_t i = tid; i < nseg; i += blockDim.x) {
-    G1Xyzz p = ld_xyzz(seg_out + (size_t)w * nseg + i);
+  for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
+    G1Xyzz p = ld_xyzz(in + (size_t)w * in_stride + i);
     xyzz_add(acc, p);
   }
   st_xyzz(&sh[tid], acc);
@@ -209,19 +228,51 @@ __global__ void __launch_bounds__(RED_THREADS) msm_window_reduce_kernel(const G1
     }
     __syncthreads();
   }
-  if (tid == 0) st_xyzz(win_out + w, ld_xyzz(&sh[0]));
+  if (tid == 0) st_xyzz(out + (size_t)w * out_stride + blockIdx.x, ld_xyzz(&sh[0]));
+}
+
+// F[w] = G[w] + A_0[w] + L (A_1[w] + L (A_2[w] + ...)); a_lvl is [levels][nsets]
+__global__ void msm_reduce_combine_kernel(const G1Xyzz* __restrict__ g, uint32_t g_stride, const G1Xyzz* __restrict__ a_lvl,
+                                          uint32_t levels, uint32_t nsets, G1Xyzz* __restrict__ out) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nsets) return;
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (int l = (int)levels - 1; l >= 0; l--) {
+    for (uint32_t k = 0; k < RED_LOG; k++) acc = xyzz_dbl(acc);
+    G1Xyzz a = ld_xyzz(a_lvl + (size_t)l * nsets + w);
+    xyzz_add(acc, a);
+  }
+  G1Xyzz gg = ld_xyzz(g + (size_t)w * g_stride);
+  xyzz_add(acc, gg);
+  st_xyzz(out + w, acc);
+}
+
+// 2^c * P for every point of one table window (fixed-base precomputation)
+__global__ void __launch_bounds__(128) msm_shift_window_kernel(const G1Affine* __restrict__ in, size_t n, uint32_t c,
+                                                               G1Xyzz* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G1Affine p = ld_affine(in + i);
+  G1Xyzz acc = G1Xyzz::infinity();
+  if (!p.is_inf()) {
+    acc = xyzz_dbl_affine(p);
+    for (uint32_t k = 1; k < c; k++) acc = xyzz_dbl(acc);
+  }
+  st_xyzz(out + i, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host orchestration
 // ------------------------------------------------------------------------------------------------
-static uint32_t choose_window_bits(size_t n) {
-  // cost model: 10 * n * W mixed adds + ~2.7 * 14 * 2^(c-1) * W reduction adds
+// cost model in mixed-add units: n*W additions + ~8 per bucket for the reduction levels
+static uint32_t choose_window_bits(size_t n, bool fixed) {
   uint32_t best = 4;
   double best_cost = 1e300;
-  for (uint32_t c = 4; c <= 20; c++) {
+  const uint32_t cmax = fixed ? 24 : 20;
+  for (uint32_t c = 4; c <= cmax; c++) {
     const uint32_t W = 255 / c + 1;
-    const double cost = 10.0 * (double)n * W + 2.7 * 14.0 * (double)(1u << (c - 1)) * W;
+    const double nb = (double)(1u << (c - 1)) * (fixed ? 1 : W);
+    const double cost = (double)n * W + 8.0 * nb;
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -316,26 +367,62 @@ static void phase_collect(Ctx* ctx) {
 #endif
 }
 
-int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G1Xyzz* out_host) {
+static int xyzz_sum_dev(Ctx* ctx, const G1Xyzz* in, uint32_t count, uint32_t in_stride, uint32_t nsets, G1Xyzz* out,
+                        uint32_t out_stride, G1Xyzz* scratch) {
+  // at most two passes: count -> <= 256 block sums -> 1
+  cudaStream_t st = ctx->stream;
+  if (count > 4 * RED_THREADS) {
+    uint32_t chunk = (count + 255) / 256;
+    if (chunk < 2 * RED_THREADS) chunk = 2 * RED_THREADS;
+    const uint32_t nblk = (count + chunk - 1) / chunk;
+    ZKP_LAUNCH(xyzz_sum_kernel, dim3(nblk, nsets), dim3(RED_THREADS), 0, st, in, count, in_stride, chunk, scratch, nblk);
+    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)scratch, nblk, nblk, nblk, out,
+               out_stride);
+    ctx->msm_launches += 2;
+  } else {
+    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, nsets), dim3(RED_THREADS), 0, st, in, count, in_stride, count, out, out_stride);
+    ctx->msm_launches += 1;
+  }
+  return ZKP_OK;
+}
+
+// `fixed`: bases is a precomputed table of nwin windows x table_stride points (see msm_precompute_dev)
+int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G1Xyzz* out_host, uint32_t fixed_c,
+                size_t table_stride) {
   ctx->msm_launches = 0;
   *out_host = G1Xyzz::infinity();
   if (n_ == 0) return ZKP_OK;  // scheme.rs:94 unwrap_or(G1Point::zero())
   if (n_ >= ((size_t)1 << 28)) return ZKP_ERR_INVALID_ARG;
+  const bool fixed = fixed_c != 0;
   const uint32_t n = (uint32_t)n_;
-  const uint32_t c = ctx->msm_window_bits ? ctx->msm_window_bits : choose_window_bits(n);
+  const uint32_t c = fixed ? fixed_c : (ctx->msm_window_bits ? ctx->msm_window_bits : choose_window_bits(n, false));
   const uint32_t nwin = 255 / c + 1;
   const uint32_t nbuckets = 1u << (c - 1);
-  const uint32_t total_buckets = nbuckets * nwin;
+  const uint32_t nsets = fixed ? 1 : nwin;
+  const uint32_t total_buckets = nbuckets * nsets;
   const size_t total = (size_t)n * nwin;
-  if (total >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
-  const uint32_t seg_log = (c - 1 < SEG_LOG) ? (c - 1) : SEG_LOG;
-  const uint32_t nseg = nbuckets >> seg_log;
-  // bound the longest run one thread owns: 4x the mean bucket load, at least 64
-  uint32_t smax = (uint32_t)((4 * (size_t)n) / nbuckets);
-  if (smax < 64) smax = 64;
+  if (total >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
+  if (fixed && (size_t)nwin * table_stride >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
+  // bound the longest run one thread owns: 4x the mean bucket load, but never so long that fewer than ~128 K
+  // tasks exist (few, heavily loaded buckets), and at least 32
+  uint32_t smax = (uint32_t)((4 * total) / total_buckets);
+  if (smax > total / 131072) smax = (uint32_t)(total / 131072);
+  if (smax < 32) smax = 32;
   const size_t max_tasks = (size_t)total_buckets + total / smax + 1;
+  // reduction levels: m_0 = nbuckets, m_(l+1) = ceil(m_l / 16) until one group is left
+  uint32_t lvl_m[MAX_RED_LEVELS], levels = 0;
+  size_t lvl_elems = 0;
+  for (uint32_t m = nbuckets;;) {
+    lvl_m[levels++] = m;
+    const uint32_t groups = (m + RED_L - 1) >> RED_LOG;
+    lvl_elems += groups;
+    if (groups == 1 || levels == MAX_RED_LEVELS) break;
+    m = groups;
+  }
 
   MsmScratch& m = ctx->msm;
+  unsigned key_bits = 1;
+  while ((1ull << key_bits) <= total_buckets) key_bits++;  // sentinel = total_buckets must be representable
   ZKP_TRY(m.keys_a.reserve(total * 4));
   ZKP_TRY(m.keys_b.reserve(total * 4));
   ZKP_TRY(m.vals_a.reserve(total * 4));
@@ -345,8 +432,8 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 8));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
-  ZKP_TRY(m.seg_out.reserve((size_t)nseg * nwin * sizeof(G1Xyzz)));
-  ZKP_TRY(m.win_out.reserve((size_t)(nwin + 1) * sizeof(G1Xyzz)));
+  ZKP_TRY(m.seg_out.reserve((2 * lvl_elems * nsets + 512 * (size_t)nsets) * sizeof(G1Xyzz)));
+  ZKP_TRY(m.win_out.reserve((size_t)(nsets * (MAX_RED_LEVELS + 1) + 1) * sizeof(G1Xyzz)));
   uint32_t* keys_a = m.keys_a.as<uint32_t>();
   uint32_t* keys_b = m.keys_b.as<uint32_t>();
   uint32_t* vals_a = m.vals_a.as<uint32_t>();
@@ -361,23 +448,22 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   uint32_t* task_len_sorted = task_id + max_tasks;
   uint32_t* task_order = task_len_sorted + max_tasks;
   G1Xyzz* partials = m.partials.as<G1Xyzz>();
-  G1Xyzz* seg_out = m.seg_out.as<G1Xyzz>();
-  G1Xyzz* win_out = m.win_out.as<G1Xyzz>();
+  G1Xyzz* lvl_buf = m.seg_out.as<G1Xyzz>();
+  G1Xyzz* a_lvl = m.win_out.as<G1Xyzz>();                 // [levels][nsets]
+  G1Xyzz* win_out = a_lvl + (size_t)MAX_RED_LEVELS * nsets;  // [nsets]
   cudaStream_t st = ctx->stream;
 
   ctx->last_window_bits = c;
   ctx->last_windows = nwin;
   // 1. recode
   phase_mark(ctx, 0);
-  ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars, n, c, nwin, keys_a, vals_a);
+  ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars, n, c, nwin, (uint32_t)table_stride,
+             fixed ? 1u : 0u, keys_a, vals_a);
   ctx->msm_launches++;
   phase_mark(ctx, 1);
-  // 2. sort each window by bucket (c bits: bucket index plus the zero-digit sentinel)
-  for (uint32_t w = 0; w < nwin; w++) {
-    ZKP_TRY(sort_window(ctx, keys_a + (size_t)w * n, keys_b + (size_t)w * n, vals_a + (size_t)w * n,
-                        vals_b + (size_t)w * n, n, c));
-    ctx->msm_launches += 3;
-  }
+  // 2. one sort of every (bucket, point) pair by global bucket id
+  ZKP_TRY(sort_window(ctx, keys_a, keys_b, vals_a, vals_b, (uint32_t)total, key_bits));
+  ctx->msm_launches += (key_bits + 7) / 8 + 1;
   phase_mark(ctx, 2);
   // 3. boundaries
   ZKP_TRY(rt::dev_memset(bstart, 0, (size_t)total_buckets * 4, st));
@@ -386,7 +472,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    ZKP_LAUNCH(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, keys_b, n, nwin, nbuckets, bstart, bend);
+    ZKP_LAUNCH(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, keys_b, total, total_buckets, bstart, bend);
     ctx->msm_launches++;
   }
   // 4. tasks
@@ -410,25 +496,79 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
                task_order, ntasks, vals_b, bases, partials);
     ctx->msm_launches += 3;
   }
-  // 6. reduce
+  // 6. reduce: base-16 digit recursion over every bucket set
   phase_mark(ctx, 4);
-  ZKP_LAUNCH(msm_segment_reduce_kernel, dim3((nseg * nwin + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
-             partials, task_off, ntask, nbuckets, nwin, seg_log, seg_out);
-  ZKP_LAUNCH(msm_window_reduce_kernel, dim3(nwin), dim3(RED_THREADS), 0, st, seg_out, nseg, win_out);
-  ctx->msm_launches += 2;
+  {
+    G1Xyzz* sum_scratch = lvl_buf + 2 * lvl_elems * nsets;
+    const G1Xyzz* cur = partials;
+    G1Xyzz* next = lvl_buf;
+    for (uint32_t l = 0; l < levels; l++) {
+      const uint32_t mm = lvl_m[l];
+      const uint32_t groups = (mm + RED_L - 1) >> RED_LOG;
+      G1Xyzz* s_out = next;
+      G1Xyzz* t_out = next + (size_t)groups * nsets;
+      ZKP_LAUNCH(msm_reduce_level_kernel, dim3((groups * nsets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
+                 cur, (const uint32_t*)task_off, (const uint32_t*)ntask, l == 0 ? 0u : 1u, mm, nsets, s_out, t_out);
+      ctx->msm_launches++;
+      ZKP_TRY(xyzz_sum_dev(ctx, t_out, groups, groups, nsets, a_lvl + (size_t)l * nsets, 1, sum_scratch));
+      cur = s_out;
+      next = t_out + (size_t)groups * nsets;
+    }
+    // the last level's S holds one element per set unless the level cap was hit (never for c <= 32)
+    const uint32_t last_groups = (lvl_m[levels - 1] + RED_L - 1) >> RED_LOG;
+    if (last_groups != 1) return ZKP_ERR_INVALID_ARG;
+    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3((nsets + 31) / 32), dim3(32), 0, st, cur, 1u, (const G1Xyzz*)a_lvl, levels,
+               nsets, win_out);
+    ctx->msm_launches++;
+  }
   phase_mark(ctx, 5);
   ZKP_TRY(rt::check_last());
-  // 7. host: Horner over windows
-  std::vector<G1Xyzz> wins(nwin);
-  ZKP_TRY(rt::d2h(wins.data(), win_out, (size_t)nwin * sizeof(G1Xyzz), st));
+  // 7. host: Horner over the window sums (windowed mode); fixed-base mode has a single bucket set
+  std::vector<G1Xyzz> wins(nsets);
+  ZKP_TRY(rt::d2h(wins.data(), win_out, (size_t)nsets * sizeof(G1Xyzz), st));
   ZKP_TRY(rt::sync(st));
   phase_collect(ctx);
-  G1Xyzz acc = wins[nwin - 1];
-  for (int w = (int)nwin - 2; w >= 0; w--) {
+  G1Xyzz acc = wins[nsets - 1];
+  for (int w = (int)nsets - 2; w >= 0; w--) {
     for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl(acc);
     xyzz_add(acc, wins[w]);
   }
   *out_host = acc;
+  return ZKP_OK;
+}
+
+// Fixed-base table for the resident SRS: window w holds 2^(c w) * srs[i].  One pass per window: c doublings
+// per point in XYZZ, then batch normalisation back to affine (gen.cu).
+int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out);
+
+int msm_precompute_dev(Ctx* ctx, uint32_t c) {
+  rt::dev_free(ctx->srs_tab);
+  ctx->srs_tab = nullptr;
+  ctx->srs_tab_c = 0;
+  const size_t n = ctx->srs_len;
+  if (n == 0) return ZKP_OK;
+  if (c == 0) c = choose_window_bits(n, true);
+  if (c < 2 || c > 26) return ZKP_ERR_INVALID_ARG;
+  const uint32_t nwin = 255 / c + 1;
+  if ((size_t)nwin * n >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(rt::dev_malloc((void**)&ctx->srs_tab, (size_t)nwin * n * sizeof(G1Affine)));
+  DevBuf tmp;
+  int st = tmp.reserve(n * sizeof(G1Xyzz));
+  if (st == ZKP_OK) st = rt::d2d(ctx->srs_tab, ctx->srs, n * sizeof(G1Affine), ctx->stream);
+  for (uint32_t w = 1; w < nwin && st == ZKP_OK; w++) {
+    ZKP_LAUNCH(msm_shift_window_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, ctx->stream,
+               (const G1Affine*)(ctx->srs_tab + (size_t)(w - 1) * n), n, c, tmp.as<G1Xyzz>());
+    st = normalise_dev(ctx, tmp.as<G1Xyzz>(), n, ctx->srs_tab + (size_t)w * n);
+  }
+  if (st == ZKP_OK) st = rt::sync(ctx->stream);
+  tmp.release();
+  if (st != ZKP_OK) {
+    rt::dev_free(ctx->srs_tab);
+    ctx->srs_tab = nullptr;
+    return st;
+  }
+  ctx->srs_tab_c = c;
+  ctx->srs_tab_windows = nwin;
   return ZKP_OK;
 }
 

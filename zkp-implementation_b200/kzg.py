@@ -94,10 +94,12 @@ class KzgScheme:
     """kzg/src/scheme.rs:22-36.  Construction uploads the SRS to HBM once; the reference instead
     clones the whole `Vec<G1Affine>` on every commit (srs.rs:78-80 at scheme.rs:85)."""
 
-    def __init__(self, engine, srs: Srs):
+    def __init__(self, engine, srs: Srs, precompute: bool = True):
         self.engine = engine
         self.srs = srs
         engine.srs_upload(srs.g1_limbs())
+        if precompute and len(srs):
+            engine.srs_precompute()  # fixed-base table: one bucket set for all windows of every commit
 
     # scheme.rs:84-96
     def _evaluate_in_s(self, coeffs: Sequence[int]) -> Point:
