@@ -104,13 +104,59 @@ __global__ void __launch_bounds__(256) msm_bounds_kernel(const uint32_t* __restr
 }
 
 // ---- 4. tasks ------------------------------------------------------------------------------------
+// heavy[0] = number of buckets split into more than HEAVY_TASKS tasks, heavy[1 + k] = their ids: their
+// partial sums are folded by a whole block each (msm_heavy_fold_kernel) before the reduction reads them
+static constexpr uint32_t HEAVY_TASKS = 4;
+static constexpr uint32_t HEAVY_CAP = 1u << 16;
+
 __global__ void __launch_bounds__(256) msm_task_count_kernel(const uint32_t* __restrict__ bstart,
                                                              const uint32_t* __restrict__ bend, uint32_t total_buckets,
-                                                             uint32_t smax, uint32_t* __restrict__ ntask) {
+                                                             uint32_t smax, uint32_t* __restrict__ ntask,
+                                                             uint32_t* __restrict__ heavy) {
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb >= total_buckets) return;
   const uint32_t len = bend[gb] - bstart[gb];
-  ntask[gb] = (len + smax - 1) / smax;
+  const uint32_t nt = (len + smax - 1) / smax;
+  ntask[gb] = nt;
+  if (nt > HEAVY_TASKS) {
+    const uint32_t slot = atomicAdd(heavy, 1u);
+    if (slot < HEAVY_CAP) heavy[1 + slot] = gb;
+  }
+}
+
+// One block per heavy bucket: partials[off] = sum of its nt partials (the reduction then reads one entry).
+__global__ void __launch_bounds__(128) msm_heavy_fold_kernel(const uint32_t* __restrict__ heavy,
+                                                             const uint32_t* __restrict__ task_off,
+                                                             const uint32_t* __restrict__ ntask,
+                                                             G1Xyzz* __restrict__ partials, uint32_t* __restrict__ nfold) {
+  __shared__ G1Xyzz sh[128];
+  const uint32_t tid = threadIdx.x;
+  uint32_t count = heavy[0];
+  if (count > HEAVY_CAP) count = HEAVY_CAP;
+  for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+    const uint32_t gb = heavy[1 + h];
+    const uint32_t nt = ntask[gb], off = task_off[gb];
+    G1Xyzz acc = G1Xyzz::infinity();
+    for (uint32_t k = tid; k < nt; k += blockDim.x) {
+      G1Xyzz p = ld_xyzz(partials + off + k);
+      xyzz_add(acc, p);
+    }
+    st_xyzz(&sh[tid], acc);
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+        G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
+        xyzz_add(a, b);
+        st_xyzz(&sh[tid], a);
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      st_xyzz(partials + off, ld_xyzz(&sh[0]));
+      nfold[gb] = 1;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __restrict__ bstart,
@@ -189,7 +235,7 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1X
     if (b < m) {
       const size_t gb = (size_t)w * m + b;
       if (in_mode == 0) {
-        const uint32_t nt = ntask[gb], off = task_off[gb];
+        const uint32_t nt = ntask[gb], off = task_off[gb];  // ntask: after msm_heavy_fold_kernel (<= HEAVY_TASKS)
         for (uint32_t k = 0; k < nt; k++) {
           G1Xyzz p = ld_xyzz(in + off + k);
           xyzz_add(run, p);
@@ -429,7 +475,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   ZKP_TRY(m.vals_b.reserve(total * 4));
   ZKP_TRY(m.bucket_start.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.bucket_end.reserve((size_t)total_buckets * 4));
-  ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 8));
+  ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
   ZKP_TRY(m.seg_out.reserve((2 * lvl_elems * nsets + 512 * (size_t)nsets) * sizeof(G1Xyzz)));
@@ -442,6 +488,8 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   uint32_t* bend = m.bucket_end.as<uint32_t>();
   uint32_t* ntask = m.misc.as<uint32_t>();
   uint32_t* task_off = ntask + (total_buckets + 1);
+  uint32_t* nfold = task_off + (total_buckets + 1);  // ntask after heavy buckets were folded to one partial
+  uint32_t* heavy = nfold + (total_buckets + 1);
   MsmTask* tasks = m.task_meta.as<MsmTask>();
   uint32_t* task_len = reinterpret_cast<uint32_t*>(tasks + max_tasks);
   uint32_t* task_id = task_len + max_tasks;
@@ -477,8 +525,9 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   }
   // 4. tasks
   ZKP_TRY(rt::dev_memset(ntask + total_buckets, 0, 4, st));
+  ZKP_TRY(rt::dev_memset(heavy, 0, 4, st));
   ZKP_LAUNCH(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, total_buckets, smax,
-             ntask);
+             ntask, heavy);
   ZKP_TRY(exclusive_scan_u32(ctx, ntask, task_off, total_buckets + 1));
   ZKP_LAUNCH(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
              total_buckets, smax, tasks, task_len, task_id);
@@ -496,8 +545,12 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
                task_order, ntasks, vals_b, bases, partials);
     ctx->msm_launches += 3;
   }
-  // 6. reduce: base-16 digit recursion over every bucket set
+  // 6. reduce: fold the partials of heavily split buckets, then the base-16 digit recursion over every bucket set
   phase_mark(ctx, 4);
+  ZKP_TRY(rt::d2d(nfold, ntask, (size_t)total_buckets * 4, st));
+  ZKP_LAUNCH(msm_heavy_fold_kernel, dim3(ctx->sm_count * 4), dim3(128), 0, st, (const uint32_t*)heavy,
+             (const uint32_t*)task_off, (const uint32_t*)ntask, partials, nfold);
+  ctx->msm_launches++;
   {
     G1Xyzz* sum_scratch = lvl_buf + 2 * lvl_elems * nsets;
     const G1Xyzz* cur = partials;
@@ -508,7 +561,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
       G1Xyzz* s_out = next;
       G1Xyzz* t_out = next + (size_t)groups * nsets;
       ZKP_LAUNCH(msm_reduce_level_kernel, dim3((groups * nsets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
-                 cur, (const uint32_t*)task_off, (const uint32_t*)ntask, l == 0 ? 0u : 1u, mm, nsets, s_out, t_out);
+                 cur, (const uint32_t*)task_off, (const uint32_t*)nfold, l == 0 ? 0u : 1u, mm, nsets, s_out, t_out);
       ctx->msm_launches++;
       ZKP_TRY(xyzz_sum_dev(ctx, t_out, groups, groups, nsets, a_lvl + (size_t)l * nsets, 1, sum_scratch));
       cur = s_out;
