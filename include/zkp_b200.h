@@ -89,6 +89,11 @@ int zkp_msm_g1_bases(zkp_ctx* ctx, const uint64_t* scalars, const uint64_t* xy, 
  * bases_dev == NULL uses the resident SRS. */
 int zkp_msm_g1_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xy[12],
                    uint8_t* out_infinity);
+/* `count` <= 16 commitments against the resident SRS in ONE pipeline (the prover's a/b/c, t_lo/t_mid/t_hi and the
+ * two opening commitments, plonk/src/prover.rs:577-579, slice_polynomial.rs:52): with the fixed-base table every
+ * MSM of the batch is one more bucket set of the same sort / accumulate / reduce launches.  out_xy: count x 12. */
+int zkp_msm_g1_multi_dev(zkp_ctx* ctx, uint32_t count, const void* const* scalars_dev, const size_t* lens, uint64_t* out_xy,
+                         uint8_t* out_infinity /* count, or NULL */);
 /* Multi-GPU point-range sharding: each rank computes the un-normalised partial sum of its shard
  * (XYZZ coordinates, 4 x 6 u64) ...                                                              */
 int zkp_msm_g1_partial_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xyzz[24]);

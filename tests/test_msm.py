@@ -135,3 +135,30 @@ def test_precompute_then_new_srs_drops_table(zkp, engine, coracle):
     engine.srs_precompute(5)
     engine.srs_upload(b2)  # a stale table would give sums over b1
     assert (engine.msm(s)[0] == coracle.msm_pippenger(s, b2)).all()
+
+
+def test_multi_msm_one_pipeline(zkp, engine, coracle):
+    """zkp_msm_g1_multi_dev: several commitments against the resident SRS as bucket sets of one pipeline
+    (with the fixed-base table) or one after the other (without) -- the same points either way, ragged lengths,
+    an all-zero vector and an empty one included."""
+    F = zkp.fields
+    n = 400
+    b = coracle.srs(F.fr_to_mont_array([0x7777]), n)
+    vecs = [F.random_fr_mont(81, n), F.random_fr_mont(82, 399), F.random_fr_mont(83, 250),
+            np.zeros((n, 4), dtype=np.uint64), F.random_fr_mont(84, 120)]
+    want = [coracle.msm_pippenger(v, b[:v.shape[0]]) for v in vecs]
+    engine.srs_upload(b)
+    for table in (False, True):
+        if table:
+            engine.srs_precompute(7)
+        dv = [engine.vec(v) for v in vecs]
+        got = engine.msm_multi_dev([d.ptr for d in dv], [v.shape[0] for v in vecs])
+        for j, (out, inf) in enumerate(got):
+            if j == 3:
+                assert inf
+            else:
+                assert (out == want[j]).all() and not inf, (table, j)
+        # with an empty member the batch falls back to one MSM at a time; the empty sum is the identity
+        got = engine.msm_multi_dev([dv[0].ptr, dv[0].ptr], [n, 0])
+        assert (got[0][0] == want[0]).all() and got[1][1]
+    engine.srs_upload(b[:1])

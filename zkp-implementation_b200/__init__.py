@@ -44,6 +44,8 @@ ABI = {
                                         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_msm_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_msm_g1_multi_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_msm_g1_partial_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                               ctypes.c_void_p]),
     "zkp_g1_fold_partials": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
@@ -218,6 +220,17 @@ class Engine:
         inf = ctypes.c_uint8(0)
         self._check(self.lib.zkp_msm_g1_dev(self._h, _ptr(scalars_dev), _ptr(bases_dev), n, _ptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
+
+    def msm_multi_dev(self, scalars_devs: Sequence, lens: Sequence[int]):
+        """Several commitments against the resident SRS as one pipeline -> list of (xy limbs, infinity)."""
+        k = len(lens)
+        ptrs = (ctypes.c_void_p * k)(*[_ptr(s) for s in scalars_devs])
+        ln = (ctypes.c_size_t * k)(*lens)
+        out = np.zeros((k, 12), dtype=np.uint64)
+        inf = np.zeros(k, dtype=np.uint8)
+        self._check(self.lib.zkp_msm_g1_multi_dev(self._h, k, ctypes.cast(ptrs, ctypes.c_void_p),
+                                                  ctypes.cast(ln, ctypes.c_void_p), _ptr(out), _ptr(inf)))
+        return [(out[j], bool(inf[j])) for j in range(k)]
 
     def msm_partial_dev(self, scalars_dev, bases_dev, n: int) -> np.ndarray:
         out = np.zeros(24, dtype=np.uint64)

@@ -218,6 +218,33 @@ int zkp_msm_g1_dev(zkp_ctx* h, const void* scalars_dev, const void* bases_dev, s
   return ZKP_OK;
 }
 
+int zkp_msm_g1_multi_dev(zkp_ctx* h, uint32_t count, const void* const* scalars_dev, const size_t* lens, uint64_t* out_xy,
+                         uint8_t* out_infinity) {
+  if (!h || (count && (!scalars_dev || !lens || !out_xy)) || count > 16) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  Ctx* c = &h->c;
+  ZKP_TRY(rt::set_device(c->device));
+  size_t shortest = (size_t)-1;
+  for (uint32_t j = 0; j < count; j++) {
+    if (lens[j] > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
+    if (lens[j] && !scalars_dev[j]) return ZKP_ERR_INVALID_ARG;
+    if (lens[j] < shortest) shortest = lens[j];
+  }
+  G1Xyzz acc[16];
+  if (count > 1 && c->srs_tab && shortest >= c->srs_len / 4) {
+    ZKP_TRY(msm_run_multi_dev(c, (const Fr* const*)scalars_dev, lens, count, c->srs_tab, acc, c->srs_tab_c, c->srs_len));
+  } else {
+    uint32_t launches = 0;
+    for (uint32_t j = 0; j < count; j++) {
+      ZKP_TRY(msm_nolock(c, scalars_dev[j], nullptr, lens[j], &acc[j]));
+      launches += c->msm_launches;
+    }
+    c->msm_launches = launches;
+  }
+  for (uint32_t j = 0; j < count; j++) write_affine(acc[j], out_xy + 12 * j, out_infinity ? out_infinity + j : nullptr);
+  return ZKP_OK;
+}
+
 int zkp_g1_fold_partials(const uint64_t* partials, size_t count, uint64_t out_xy[12], uint8_t* out_infinity) {
   if (!out_xy || (count && !partials)) return ZKP_ERR_INVALID_ARG;
   G1Xyzz acc = G1Xyzz::infinity();

@@ -114,6 +114,9 @@ int ntt_dist_permute_dev(Ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, uint32
 // fixed_c != 0: `bases_dev` is a fixed-base table built for window width fixed_c (windows table_stride apart)
 int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size_t n, G1Xyzz* out_host,
                 uint32_t fixed_c = 0, size_t table_stride = 0);
+// several MSMs over the same fixed-base table as ONE pipeline (one sort, one accumulate, one reduction)
+int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_list, uint32_t count, const G1Affine* bases,
+                      G1Xyzz* out_host, uint32_t fixed_c, size_t table_stride);
 int msm_precompute_dev(Ctx* ctx, uint32_t window_bits);
 void msm_destroy(Ctx* ctx);
 

@@ -50,9 +50,12 @@ struct MsmTask {
 // keys[w*n + i] = global bucket id of digit w of scalar i (weight |digit| = id within the set + 1), or the
 //                 sentinel `total_buckets` for a zero digit
 // vals[w*n + i] = base index | sign << 31; fixed-base mode: index (w * table_stride + i) into the table
+// `set`: fixed-base batches run several MSMs in one pipeline, MSM j owning bucket set j; `sentinel` = total
+// number of buckets of the whole batch.
 __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ scalars, uint32_t n, uint32_t c,
                                                          uint32_t nwin, uint32_t table_stride, uint32_t fixed,
-                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         uint32_t set, uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + i);
@@ -62,7 +65,6 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ 
   s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
   s = fp_from_mont(s);  // `cof.into_bigint()` inside ark-ec's scalar mul (scheme.rs:92)
   const uint32_t nbuckets = 1u << (c - 1);
-  const uint32_t sentinel = fixed ? nbuckets : nbuckets * nwin;
   const uint32_t cmask = (1u << c) - 1;
   uint32_t carry = 0;
   for (uint32_t w = 0; w < nwin; w++) {
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const Fr* __restrict__ 
       carry = 0;
     }
     const size_t o = (size_t)w * n + i;
-    keys[o] = d ? ((fixed ? 0u : w * nbuckets) + d - 1) : sentinel;
+    keys[o] = d ? ((fixed ? set * nbuckets : w * nbuckets) + d - 1) : sentinel;
     vals[o] = ((fixed ? w * table_stride : 0u) + i) | (neg && d ? SIGN_BIT : 0u);
   }
 }
@@ -277,6 +279,45 @@ __global__ void __launch_bounds__(RED_THREADS) xyzz_sum_kernel(const G1Xyzz* __r
   if (tid == 0) st_xyzz(out + (size_t)w * out_stride + blockIdx.x, ld_xyzz(&sh[0]));
 }
 
+// A_l for every level in two launches: block (bx, y = l * nsets + w) sums chunk bx of level l's T array of set w
+struct RedLevels {
+  uint32_t off[MAX_RED_LEVELS];     // element offset of the level's T array (layout [set][group])
+  uint32_t groups[MAX_RED_LEVELS];
+};
+static constexpr uint32_t SUM_CHUNKS = 64;
+
+__global__ void __launch_bounds__(RED_THREADS) xyzz_level_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
+                                                                     uint32_t nsets, G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[RED_THREADS];
+  const uint32_t l = blockIdx.y / nsets, w = blockIdx.y - l * nsets, tid = threadIdx.x;
+  const uint32_t count = lv.groups[l];
+  uint32_t chunk = (count + gridDim.x - 1) / gridDim.x;
+  if (chunk < 4 * RED_THREADS) chunk = 4 * RED_THREADS;  // short arrays: fewer, fuller blocks
+  const uint32_t lo = blockIdx.x * chunk;
+  if (lo >= count) {  // block-uniform: nothing to sum
+    if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, G1Xyzz::infinity());
+    return;
+  }
+  const uint32_t hi = (lo + chunk < count) ? lo + chunk : count;
+  const G1Xyzz* in = buf + lv.off[l] + (size_t)w * count;
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
+    G1Xyzz p = ld_xyzz(in + i);
+    xyzz_add(acc, p);
+  }
+  st_xyzz(&sh[tid], acc);
+  __syncthreads();
+  for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
+      xyzz_add(a, b);
+      st_xyzz(&sh[tid], a);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz(&sh[0]));
+}
+
 // F[w] = G[w] + A_0[w] + L (A_1[w] + L (A_2[w] + ...)); a_lvl is [levels][nsets]
 __global__ void msm_reduce_combine_kernel(const G1Xyzz* __restrict__ g, uint32_t g_stride, const G1Xyzz* __restrict__ a_lvl,
                                           uint32_t levels, uint32_t nsets, G1Xyzz* __restrict__ out) {
@@ -413,40 +454,34 @@ static void phase_collect(Ctx* ctx) {
 #endif
 }
 
-static int xyzz_sum_dev(Ctx* ctx, const G1Xyzz* in, uint32_t count, uint32_t in_stride, uint32_t nsets, G1Xyzz* out,
-                        uint32_t out_stride, G1Xyzz* scratch) {
-  // at most two passes: count -> <= 256 block sums -> 1
-  cudaStream_t st = ctx->stream;
-  if (count > 4 * RED_THREADS) {
-    uint32_t chunk = (count + 255) / 256;
-    if (chunk < 2 * RED_THREADS) chunk = 2 * RED_THREADS;
-    const uint32_t nblk = (count + chunk - 1) / chunk;
-    ZKP_LAUNCH(xyzz_sum_kernel, dim3(nblk, nsets), dim3(RED_THREADS), 0, st, in, count, in_stride, chunk, scratch, nblk);
-    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)scratch, nblk, nblk, nblk, out,
-               out_stride);
-    ctx->msm_launches += 2;
-  } else {
-    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, nsets), dim3(RED_THREADS), 0, st, in, count, in_stride, count, out, out_stride);
-    ctx->msm_launches += 1;
-  }
-  return ZKP_OK;
+int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n, G1Xyzz* out_host, uint32_t fixed_c,
+                size_t table_stride) {
+  return msm_run_multi_dev(ctx, &scalars, &n, 1, bases, out_host, fixed_c, table_stride);
 }
 
-// `fixed`: bases is a precomputed table of nwin windows x table_stride points (see msm_precompute_dev)
-int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G1Xyzz* out_host, uint32_t fixed_c,
-                size_t table_stride) {
+// `fixed_c != 0`: bases is a precomputed table of nwin windows x table_stride points (msm_precompute_dev) and
+// `count` MSMs over it run as one pipeline (MSM j = bucket set j).  Windowed mode takes count == 1.
+int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_list, uint32_t count, const G1Affine* bases,
+                      G1Xyzz* out_host, uint32_t fixed_c, size_t table_stride) {
   ctx->msm_launches = 0;
-  *out_host = G1Xyzz::infinity();
-  if (n_ == 0) return ZKP_OK;  // scheme.rs:94 unwrap_or(G1Point::zero())
-  if (n_ >= ((size_t)1 << 28)) return ZKP_ERR_INVALID_ARG;
   const bool fixed = fixed_c != 0;
-  const uint32_t n = (uint32_t)n_;
-  const uint32_t c = fixed ? fixed_c : (ctx->msm_window_bits ? ctx->msm_window_bits : choose_window_bits(n, false));
+  if (count == 0) return ZKP_OK;
+  if (!fixed && count != 1) return ZKP_ERR_INVALID_ARG;
+  size_t n_sum = 0, n_max = 0;
+  for (uint32_t j = 0; j < count; j++) {
+    out_host[j] = G1Xyzz::infinity();
+    if (n_list[j] >= ((size_t)1 << 28)) return ZKP_ERR_INVALID_ARG;
+    n_sum += n_list[j];
+    if (n_list[j] > n_max) n_max = n_list[j];
+  }
+  if (n_sum == 0) return ZKP_OK;  // scheme.rs:94 unwrap_or(G1Point::zero())
+  const uint32_t c = fixed ? fixed_c : (ctx->msm_window_bits ? ctx->msm_window_bits : choose_window_bits(n_max, false));
   const uint32_t nwin = 255 / c + 1;
   const uint32_t nbuckets = 1u << (c - 1);
-  const uint32_t nsets = fixed ? 1 : nwin;
+  const uint32_t nsets = fixed ? count : nwin;
+  if ((size_t)nbuckets * nsets >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
   const uint32_t total_buckets = nbuckets * nsets;
-  const size_t total = (size_t)n * nwin;
+  const size_t total = n_sum * nwin;
   if (total >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
   if (fixed && (size_t)nwin * table_stride >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
   // bound the longest run one thread owns: 4x the mean bucket load, but never so long that fewer than ~128 K
@@ -478,7 +513,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
-  ZKP_TRY(m.seg_out.reserve((2 * lvl_elems * nsets + 512 * (size_t)nsets) * sizeof(G1Xyzz)));
+  ZKP_TRY(m.seg_out.reserve((2 * lvl_elems * nsets + (size_t)SUM_CHUNKS * MAX_RED_LEVELS * nsets) * sizeof(G1Xyzz)));
   ZKP_TRY(m.win_out.reserve((size_t)(nsets * (MAX_RED_LEVELS + 1) + 1) * sizeof(G1Xyzz)));
   uint32_t* keys_a = m.keys_a.as<uint32_t>();
   uint32_t* keys_b = m.keys_b.as<uint32_t>();
@@ -505,9 +540,17 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   ctx->last_windows = nwin;
   // 1. recode
   phase_mark(ctx, 0);
-  ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars, n, c, nwin, (uint32_t)table_stride,
-             fixed ? 1u : 0u, keys_a, vals_a);
-  ctx->msm_launches++;
+  {
+    size_t off = 0;
+    for (uint32_t j = 0; j < count; j++) {
+      const uint32_t n = (uint32_t)n_list[j];
+      if (!n) continue;
+      ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars_list[j], n, c, nwin,
+                 (uint32_t)table_stride, fixed ? 1u : 0u, j, total_buckets, keys_a + off, vals_a + off);
+      ctx->msm_launches++;
+      off += (size_t)n * nwin;
+    }
+  }
   phase_mark(ctx, 1);
   // 2. one sort of every (bucket, point) pair by global bucket id
   ZKP_TRY(sort_window(ctx, keys_a, keys_b, vals_a, vals_b, (uint32_t)total, key_bits));
@@ -555,6 +598,8 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
     G1Xyzz* sum_scratch = lvl_buf + 2 * lvl_elems * nsets;
     const G1Xyzz* cur = partials;
     G1Xyzz* next = lvl_buf;
+    RedLevels lv;
+    memset(&lv, 0, sizeof(lv));
     for (uint32_t l = 0; l < levels; l++) {
       const uint32_t mm = lvl_m[l];
       const uint32_t groups = (mm + RED_L - 1) >> RED_LOG;
@@ -563,10 +608,19 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
       ZKP_LAUNCH(msm_reduce_level_kernel, dim3((groups * nsets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
                  cur, (const uint32_t*)task_off, (const uint32_t*)nfold, l == 0 ? 0u : 1u, mm, nsets, s_out, t_out);
       ctx->msm_launches++;
-      ZKP_TRY(xyzz_sum_dev(ctx, t_out, groups, groups, nsets, a_lvl + (size_t)l * nsets, 1, sum_scratch));
+      lv.off[l] = (uint32_t)(t_out - lvl_buf);
+      lv.groups[l] = groups;
       cur = s_out;
       next = t_out + (size_t)groups * nsets;
     }
+    // A_l = sum of level l's T array, all levels and sets in two launches
+    uint32_t chunks = (lv.groups[0] + 4 * RED_THREADS - 1) / (4 * RED_THREADS);
+    if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
+    ZKP_LAUNCH(xyzz_level_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
+               nsets, sum_scratch);
+    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)sum_scratch, chunks, chunks,
+               chunks, a_lvl, 1u);
+    ctx->msm_launches += 2;
     // the last level's S holds one element per set unless the level cap was hit (never for c <= 32)
     const uint32_t last_groups = (lvl_m[levels - 1] + RED_L - 1) >> RED_LOG;
     if (last_groups != 1) return ZKP_ERR_INVALID_ARG;
@@ -576,17 +630,21 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n_, G
   }
   phase_mark(ctx, 5);
   ZKP_TRY(rt::check_last());
-  // 7. host: Horner over the window sums (windowed mode); fixed-base mode has a single bucket set
+  // 7. host: Horner over the window sums (windowed mode); in fixed-base mode set j IS the result of MSM j
   std::vector<G1Xyzz> wins(nsets);
   ZKP_TRY(rt::d2h(wins.data(), win_out, (size_t)nsets * sizeof(G1Xyzz), st));
   ZKP_TRY(rt::sync(st));
   phase_collect(ctx);
+  if (fixed) {
+    for (uint32_t j = 0; j < count; j++) out_host[j] = wins[j];
+    return ZKP_OK;
+  }
   G1Xyzz acc = wins[nsets - 1];
   for (int w = (int)nsets - 2; w >= 0; w--) {
     for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl(acc);
     xyzz_add(acc, wins[w]);
   }
-  *out_host = acc;
+  out_host[0] = acc;
   return ZKP_OK;
 }
 

@@ -554,6 +554,14 @@ int dev_commit(zkp_ctx* ctx, const Fr* scalars_dev, size_t len, G1& out, DevTime
   return st;
 }
 
+// several commitments against the resident SRS as one MSM pipeline (zkp_msm_g1_multi_dev)
+int dev_commit_multi(zkp_ctx* ctx, uint32_t count, const Fr* const* scalars_dev, const size_t* lens, G1* out, DevTimers& tm) {
+  auto t = std::chrono::steady_clock::now();
+  int st = zkp_msm_g1_multi_dev(ctx, count, (const void* const*)scalars_dev, lens, out[0].xy, nullptr);
+  tm.msm += Timers::since(t);
+  return st;
+}
+
 // (poly - poly(root)) / (X - root) in place on the device: weight by root^i, suffix sums, unweight.
 // On return the quotient (len - 1 coefficients) starts at data + 1; *rem_zero tells whether the remainder
 // vanished (prover.rs:228-240 / 248-260 assert it).
@@ -599,7 +607,11 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
     const size_t idx[4] = {0, 1, n, n + 1};
     const Fr vals[4] = {-lo, -hi, lo, hi};
     PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.coef(k), 4, idx, vals[0].v));
-    PLONK_TRY(dev_commit(ctx, wk.coef(k), n + 2, cm[k], tm));
+  }
+  {
+    const Fr* polys[3] = {wk.coef(0), wk.coef(1), wk.coef(2)};
+    const size_t lens[3] = {n + 2, n + 2, n + 2};
+    PLONK_TRY(dev_commit_multi(ctx, 3, polys, lens, &cm[0], tm));  // commit_round1 (prover.rs:571-581)
   }
 
   // ---- Round 2 (prover.rs:98-123, 302-377) ----
@@ -683,10 +695,14 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
   if (tmp * 3 < t_len) tmp++;
   if (tmp == 0) return ZKP_B200_ERR_EMPTY_POLY;  // `chunks(0)` panics in the reference
   size_t slice_len[3];
-  for (int i = 0; i < 3; i++) {
-    const size_t lo = std::min(t_len, (size_t)i * tmp), hi = std::min(t_len, (size_t)(i + 1) * tmp);
-    slice_len[i] = hi - lo;
-    PLONK_TRY(dev_commit(ctx, wk.t() + lo, slice_len[i], cm[4 + i], tm));
+  {
+    const Fr* polys[3];
+    for (int i = 0; i < 3; i++) {
+      const size_t lo = std::min(t_len, (size_t)i * tmp), hi = std::min(t_len, (size_t)(i + 1) * tmp);
+      slice_len[i] = hi - lo;
+      polys[i] = wk.t() + lo;
+    }
+    PLONK_TRY(dev_commit_multi(ctx, 3, polys, slice_len, &cm[4], tm));  // SlicePoly::commit (slice_polynomial.rs:51-53)
   }
   const uint64_t degree = (uint64_t)tmp - 1;
 
@@ -749,7 +765,6 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
     PLONK_TRY(zkp_fr_lincomb_dev(ctx, wk.wx(), r_len, 6, polys, lens, coefs[0].v, c0.v));
     PLONK_TRY(dev_divide_linear(ctx, wk, wk.wx(), r_len, zeta, &rem_ok));
     if (!rem_ok) return ZKP_PLONK_ERR_REMAINDER;  // "w_ev_x was computed incorrectly"
-    PLONK_TRY(dev_commit(ctx, wk.wx() + 1, r_len - 1, cm[7], tm));
   }
   {
     PLONK_TRY(zkp_dev_copy(ctx, wk.wwx(), wk.coef(3), (n + 3) * 32));
@@ -758,7 +773,9 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
     PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.wwx(), 1, idx, vals[0].v));
     PLONK_TRY(dev_divide_linear(ctx, wk, wk.wwx(), n + 3, zeta_w, &rem_ok));
     if (!rem_ok) return ZKP_PLONK_ERR_REMAINDER;  // "w_ev_wx was computed incorrectly"
-    PLONK_TRY(dev_commit(ctx, wk.wwx() + 1, n + 2, cm[8], tm));
+    const Fr* polys[2] = {wk.wx() + 1, wk.wwx() + 1};
+    const size_t lens[2] = {r_len - 1, n + 2};
+    PLONK_TRY(dev_commit_multi(ctx, 2, polys, lens, &cm[7], tm));
   }
   ch.feed(cm[7]); ch.feed(cm[8]);
   Fr u;
