@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) msm_bounds_kernel(const uint32_t* __restr
 // ---- 4. tasks ------------------------------------------------------------------------------------
 // heavy[0] = number of buckets split into more than HEAVY_TASKS tasks, heavy[1 + k] = their ids: their
 // partial sums are folded by a whole block each (msm_heavy_fold_kernel) before the reduction reads them
-static constexpr uint32_t HEAVY_TASKS = 4;
+static constexpr uint32_t HEAVY_TASKS = 24;
 static constexpr uint32_t HEAVY_CAP = 1u << 16;
 
 __global__ void __launch_bounds__(256) msm_task_count_kernel(const uint32_t* __restrict__ bstart,
@@ -210,99 +210,65 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTa
 }
 
 // ---- 6. reduce -----------------------------------------------------------------------------------
-// F = sum_b (b + 1) B_b over one bucket set.  Write b in base L = 2^RED_LOG: b + 1 = 1 + sum_l d_l(b) L^l, so
-//   F = G + sum_l L^l A_l,   G = sum_b B_b,   A_l = sum_b d_l(b) B_b.
-// Level l works on the array X^l (X^0 = buckets, X^(l+1)[g] = sum of the L elements of group g of X^l): one
-// thread per group does a running sum, producing S[g] = X^(l+1)[g] and T[g] = sum_j j X^l[gL + j]; A_l is the
-// sum of T over the groups (xyzz_sum_kernel).  The last level has one group, whose S is G.
-static constexpr uint32_t RED_LOG = 4;
-static constexpr uint32_t RED_L = 1u << RED_LOG;
-static constexpr uint32_t MAX_RED_LEVELS = 8;
+// F = sum_b (b + 1) B_b over one bucket set of m = 2^(c-1) buckets, by bit planes of the bucket index:
+//   F = G + sum_l 2^l A_l,   G = sum_b B_b,   A_l = sum of the buckets whose index has bit l set.
+// Level l halves the array: X^(l+1)[g] = X^l[2g] + X^l[2g+1] (X^0 = buckets), and A_l is the sum of the odd
+// entries of X^l.  Every level is one independent addition per thread, so the serial depth is c - 1 additions
+// however many buckets there are -- the reduction stays short for the small bucket sets of small MSMs and is
+// throughput-bound (2m additions in all) for the large ones.
+static constexpr uint32_t MAX_RED_LEVELS = 26;
 
-// in_mode 0: element b of bucket set w is the sum of the partials of global bucket w*m + b (tasks of a split
-// bucket); in_mode 1: element = in[w*m + b].
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1Xyzz* __restrict__ in,
-                                                                       const uint32_t* __restrict__ task_off,
-                                                                       const uint32_t* __restrict__ ntask, uint32_t in_mode,
-                                                                       uint32_t m, uint32_t nsets, G1Xyzz* __restrict__ s_out,
-                                                                       G1Xyzz* __restrict__ t_out) {
-  const uint32_t groups = (m + RED_L - 1) >> RED_LOG;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= groups * nsets) return;
-  const uint32_t w = t / groups, g = t - w * groups;
-  const uint32_t lo = g << RED_LOG;
-  G1Xyzz run = G1Xyzz::infinity(), tot = G1Xyzz::infinity();
-  for (int j = (int)RED_L - 1; j >= 0; j--) {
-    const uint32_t b = lo + (uint32_t)j;
-    if (b < m) {
-      const size_t gb = (size_t)w * m + b;
-      if (in_mode == 0) {
-        const uint32_t nt = ntask[gb], off = task_off[gb];  // ntask: after msm_heavy_fold_kernel (<= HEAVY_TASKS)
-        for (uint32_t k = 0; k < nt; k++) {
-          G1Xyzz p = ld_xyzz(in + off + k);
-          xyzz_add(run, p);
-        }
-      } else {
-        G1Xyzz p = ld_xyzz(in + gb);
-        xyzz_add(run, p);
-      }
-    }
-    if (j > 0) xyzz_add(tot, run);  // element j ends up counted j times
-  }
-  st_xyzz(s_out + t, run);
-  st_xyzz(t_out + t, tot);
-}
-
-// out[w * out_stride + bx] = sum of in[w * in_stride + bx * chunk ... + chunk) (clipped to count)
-__global__ void __launch_bounds__(RED_THREADS) xyzz_sum_kernel(const G1Xyzz* __restrict__ in, uint32_t count,
-                                                               uint32_t in_stride, uint32_t chunk, G1Xyzz* __restrict__ out,
-                                                               uint32_t out_stride) {
-  __shared__ G1Xyzz sh[RED_THREADS];
-  const uint32_t w = blockIdx.y, tid = threadIdx.x;
-  const uint32_t lo = blockIdx.x * chunk;
-  const uint32_t hi = (lo + chunk < count) ? lo + chunk : count;
+// X^0[gb] = sum of the bucket's partial sums (tasks of a split bucket; heavily split ones were folded first)
+__global__ void __launch_bounds__(RED_THREADS) msm_bucket_gather_kernel(const G1Xyzz* __restrict__ partials,
+                                                                        const uint32_t* __restrict__ task_off,
+                                                                        const uint32_t* __restrict__ nfold,
+                                                                        uint32_t total_buckets, G1Xyzz* __restrict__ x0) {
+  const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= total_buckets) return;
+  const uint32_t nt = nfold[gb], off = task_off[gb];
   G1Xyzz acc = G1Xyzz::infinity();
-  for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
-    G1Xyzz p = ld_xyzz(in + (size_t)w * in_stride + i);
+  for (uint32_t k = 0; k < nt; k++) {
+    G1Xyzz p = ld_xyzz(partials + off + k);
     xyzz_add(acc, p);
   }
-  st_xyzz(&sh[tid], acc);
-  __syncthreads();
-  for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
-      xyzz_add(a, b);
-      st_xyzz(&sh[tid], a);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) st_xyzz(out + (size_t)w * out_stride + blockIdx.x, ld_xyzz(&sh[0]));
+  st_xyzz(x0 + gb, acc);
 }
 
-// A_l for every level in two launches: block (bx, y = l * nsets + w) sums chunk bx of level l's T array of set w
+// out[i] = in[2i] + in[2i+1] over the concatenated sets (every set has an even number of entries)
+__global__ void __launch_bounds__(RED_THREADS) msm_pair_add_kernel(const G1Xyzz* __restrict__ in, uint32_t pairs,
+                                                                   G1Xyzz* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pairs) return;
+  G1Xyzz a = ld_xyzz(in + 2 * (size_t)i);
+  const G1Xyzz b = ld_xyzz(in + 2 * (size_t)i + 1);
+  xyzz_add(a, b);
+  st_xyzz(out + i, a);
+}
+
+// A_l partial sums: block (bx, y = l * nsets + w) sums a chunk of the odd entries of X^l of set w
 struct RedLevels {
-  uint32_t off[MAX_RED_LEVELS];     // element offset of the level's T array (layout [set][group])
-  uint32_t groups[MAX_RED_LEVELS];
+  uint32_t off[MAX_RED_LEVELS];  // element offset of X^l (layout [set][m_l])
+  uint32_t m[MAX_RED_LEVELS];    // entries per set at level l
 };
 static constexpr uint32_t SUM_CHUNKS = 64;
 
-__global__ void __launch_bounds__(RED_THREADS) xyzz_level_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
-                                                                     uint32_t nsets, G1Xyzz* __restrict__ out) {
+__global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
+                                                                    uint32_t nsets, G1Xyzz* __restrict__ out) {
   __shared__ G1Xyzz sh[RED_THREADS];
   const uint32_t l = blockIdx.y / nsets, w = blockIdx.y - l * nsets, tid = threadIdx.x;
-  const uint32_t count = lv.groups[l];
+  const uint32_t count = lv.m[l] >> 1;  // odd entries
   uint32_t chunk = (count + gridDim.x - 1) / gridDim.x;
-  if (chunk < 4 * RED_THREADS) chunk = 4 * RED_THREADS;  // short arrays: fewer, fuller blocks
+  if (chunk < 2 * RED_THREADS) chunk = 2 * RED_THREADS;  // short arrays: fewer, fuller blocks
   const uint32_t lo = blockIdx.x * chunk;
   if (lo >= count) {  // block-uniform: nothing to sum
     if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, G1Xyzz::infinity());
     return;
   }
   const uint32_t hi = (lo + chunk < count) ? lo + chunk : count;
-  const G1Xyzz* in = buf + lv.off[l] + (size_t)w * count;
+  const G1Xyzz* in = buf + lv.off[l] + (size_t)w * lv.m[l];
   G1Xyzz acc = G1Xyzz::infinity();
   for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
-    G1Xyzz p = ld_xyzz(in + i);
+    G1Xyzz p = ld_xyzz(in + 2 * (size_t)i + 1);
     xyzz_add(acc, p);
   }
   st_xyzz(&sh[tid], acc);
@@ -318,20 +284,35 @@ __global__ void __launch_bounds__(RED_THREADS) xyzz_level_sum_kernel(const G1Xyz
   if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz(&sh[0]));
 }
 
-// F[w] = G[w] + A_0[w] + L (A_1[w] + L (A_2[w] + ...)); a_lvl is [levels][nsets]
-__global__ void msm_reduce_combine_kernel(const G1Xyzz* __restrict__ g, uint32_t g_stride, const G1Xyzz* __restrict__ a_lvl,
-                                          uint32_t levels, uint32_t nsets, G1Xyzz* __restrict__ out) {
-  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nsets) return;
+// F[w] = G[w] + sum_l 2^l A_l[w]: one block per set, thread l doubles (sum of its plane's chunk sums) l times,
+// then a tree over the planes.  part is [levels * nsets][chunks]; g points at X^levels (one entry per set).
+__global__ void __launch_bounds__(32) msm_reduce_combine_kernel(const G1Xyzz* __restrict__ part, uint32_t chunks,
+                                                                const G1Xyzz* __restrict__ g, uint32_t levels, uint32_t nsets,
+                                                                G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[32];
+  const uint32_t w = blockIdx.x, l = threadIdx.x;
   G1Xyzz acc = G1Xyzz::infinity();
-  for (int l = (int)levels - 1; l >= 0; l--) {
-    for (uint32_t k = 0; k < RED_LOG; k++) acc = xyzz_dbl(acc);
-    G1Xyzz a = ld_xyzz(a_lvl + (size_t)l * nsets + w);
-    xyzz_add(acc, a);
+  if (l < levels) {
+    const G1Xyzz* p = part + ((size_t)l * nsets + w) * chunks;
+    for (uint32_t k = 0; k < chunks; k++) {
+      G1Xyzz q = ld_xyzz(p + k);
+      xyzz_add(acc, q);
+    }
+    for (uint32_t k = 0; k < l; k++) acc = xyzz_dbl(acc);
+  } else if (l == levels) {
+    acc = ld_xyzz(g + w);
   }
-  G1Xyzz gg = ld_xyzz(g + (size_t)w * g_stride);
-  xyzz_add(acc, gg);
-  st_xyzz(out + w, acc);
+  st_xyzz(&sh[l], acc);
+  __syncthreads();
+  for (uint32_t s = 16; s > 0; s >>= 1) {
+    if (l < s) {
+      G1Xyzz a = ld_xyzz(&sh[l]), b = ld_xyzz(&sh[l + s]);
+      xyzz_add(a, b);
+      st_xyzz(&sh[l], a);
+    }
+    __syncthreads();
+  }
+  if (l == 0) st_xyzz(out + w, ld_xyzz(&sh[0]));
 }
 
 // 2^c * P for every point of one table window (fixed-base precomputation)
@@ -490,16 +471,10 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   if (smax > total / 131072) smax = (uint32_t)(total / 131072);
   if (smax < 32) smax = 32;
   const size_t max_tasks = (size_t)total_buckets + total / smax + 1;
-  // reduction levels: m_0 = nbuckets, m_(l+1) = ceil(m_l / 16) until one group is left
-  uint32_t lvl_m[MAX_RED_LEVELS], levels = 0;
-  size_t lvl_elems = 0;
-  for (uint32_t m = nbuckets;;) {
-    lvl_m[levels++] = m;
-    const uint32_t groups = (m + RED_L - 1) >> RED_LOG;
-    lvl_elems += groups;
-    if (groups == 1 || levels == MAX_RED_LEVELS) break;
-    m = groups;
-  }
+  // reduction levels: X^l has nbuckets >> l entries per set, l = 0 .. c - 1 (the last one is G)
+  const uint32_t levels = c - 1;
+  if (levels + 1 > 32 || levels > MAX_RED_LEVELS) return ZKP_ERR_INVALID_ARG;
+  const size_t lvl_elems = 2 * (size_t)nbuckets;  // sum over l of nbuckets >> l, per set
 
   MsmScratch& m = ctx->msm;
   unsigned key_bits = 1;
@@ -513,8 +488,8 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
-  ZKP_TRY(m.seg_out.reserve((2 * lvl_elems * nsets + (size_t)SUM_CHUNKS * MAX_RED_LEVELS * nsets) * sizeof(G1Xyzz)));
-  ZKP_TRY(m.win_out.reserve((size_t)(nsets * (MAX_RED_LEVELS + 1) + 1) * sizeof(G1Xyzz)));
+  ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + (size_t)SUM_CHUNKS * MAX_RED_LEVELS * nsets) * sizeof(G1Xyzz)));
+  ZKP_TRY(m.win_out.reserve((size_t)(nsets + 1) * sizeof(G1Xyzz)));
   uint32_t* keys_a = m.keys_a.as<uint32_t>();
   uint32_t* keys_b = m.keys_b.as<uint32_t>();
   uint32_t* vals_a = m.vals_a.as<uint32_t>();
@@ -532,8 +507,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   uint32_t* task_order = task_len_sorted + max_tasks;
   G1Xyzz* partials = m.partials.as<G1Xyzz>();
   G1Xyzz* lvl_buf = m.seg_out.as<G1Xyzz>();
-  G1Xyzz* a_lvl = m.win_out.as<G1Xyzz>();                 // [levels][nsets]
-  G1Xyzz* win_out = a_lvl + (size_t)MAX_RED_LEVELS * nsets;  // [nsets]
+  G1Xyzz* win_out = m.win_out.as<G1Xyzz>();  // [nsets]
   cudaStream_t st = ctx->stream;
 
   ctx->last_window_bits = c;
@@ -588,44 +562,40 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
                task_order, ntasks, vals_b, bases, partials);
     ctx->msm_launches += 3;
   }
-  // 6. reduce: fold the partials of heavily split buckets, then the base-16 digit recursion over every bucket set
+  // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
   phase_mark(ctx, 4);
   ZKP_TRY(rt::d2d(nfold, ntask, (size_t)total_buckets * 4, st));
   ZKP_LAUNCH(msm_heavy_fold_kernel, dim3(ctx->sm_count * 4), dim3(128), 0, st, (const uint32_t*)heavy,
              (const uint32_t*)task_off, (const uint32_t*)ntask, partials, nfold);
-  ctx->msm_launches++;
+  ZKP_LAUNCH(msm_bucket_gather_kernel, dim3((total_buckets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
+             (const G1Xyzz*)partials, (const uint32_t*)task_off, (const uint32_t*)nfold, total_buckets, lvl_buf);
+  ctx->msm_launches += 2;
   {
-    G1Xyzz* sum_scratch = lvl_buf + 2 * lvl_elems * nsets;
-    const G1Xyzz* cur = partials;
-    G1Xyzz* next = lvl_buf;
+    G1Xyzz* sum_scratch = lvl_buf + lvl_elems * nsets;
     RedLevels lv;
     memset(&lv, 0, sizeof(lv));
+    size_t off = 0;
     for (uint32_t l = 0; l < levels; l++) {
-      const uint32_t mm = lvl_m[l];
-      const uint32_t groups = (mm + RED_L - 1) >> RED_LOG;
-      G1Xyzz* s_out = next;
-      G1Xyzz* t_out = next + (size_t)groups * nsets;
-      ZKP_LAUNCH(msm_reduce_level_kernel, dim3((groups * nsets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
-                 cur, (const uint32_t*)task_off, (const uint32_t*)nfold, l == 0 ? 0u : 1u, mm, nsets, s_out, t_out);
+      const uint32_t mm = nbuckets >> l;
+      lv.off[l] = (uint32_t)off;
+      lv.m[l] = mm;
+      const uint32_t pairs = (mm >> 1) * nsets;
+      ZKP_LAUNCH(msm_pair_add_kernel, dim3((pairs + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
+                 (const G1Xyzz*)(lvl_buf + off), pairs, lvl_buf + off + (size_t)mm * nsets);
       ctx->msm_launches++;
-      lv.off[l] = (uint32_t)(t_out - lvl_buf);
-      lv.groups[l] = groups;
-      cur = s_out;
-      next = t_out + (size_t)groups * nsets;
+      off += (size_t)mm * nsets;
     }
-    // A_l = sum of level l's T array, all levels and sets in two launches
-    uint32_t chunks = (lv.groups[0] + 4 * RED_THREADS - 1) / (4 * RED_THREADS);
+    // A_l = sum of the odd entries of X^l, every level and set in one launch; the combine finishes the sums
+    uint32_t chunks = ((nbuckets >> 1) + 2 * RED_THREADS - 1) / (2 * RED_THREADS);
     if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
-    ZKP_LAUNCH(xyzz_level_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
-               nsets, sum_scratch);
-    ZKP_LAUNCH(xyzz_sum_kernel, dim3(1, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)sum_scratch, chunks, chunks,
-               chunks, a_lvl, 1u);
-    ctx->msm_launches += 2;
-    // the last level's S holds one element per set unless the level cap was hit (never for c <= 32)
-    const uint32_t last_groups = (lvl_m[levels - 1] + RED_L - 1) >> RED_LOG;
-    if (last_groups != 1) return ZKP_ERR_INVALID_ARG;
-    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3((nsets + 31) / 32), dim3(32), 0, st, cur, 1u, (const G1Xyzz*)a_lvl, levels,
-               nsets, win_out);
+    if (chunks < 1) chunks = 1;
+    if (levels) {
+      ZKP_LAUNCH(msm_plane_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
+                 nsets, sum_scratch);
+      ctx->msm_launches++;
+    }
+    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3(nsets), dim3(32), 0, st, (const G1Xyzz*)sum_scratch, chunks,
+               (const G1Xyzz*)(lvl_buf + off), levels, nsets, win_out);
     ctx->msm_launches++;
   }
   phase_mark(ctx, 5);
