@@ -5,10 +5,12 @@ at 2^24 ...; 1/2/4/8 B200").
     python bench.py --gpus N --steps K --warmup W            # this engine (CUDA, sm_100a)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
 
-One "step" = one 2^24-point G1 MSM on one batch of synthetic input (random scalars, distinct
-pseudo-random bases generated on the device).  At N > 1 every rank owns a 2^24-point shard of an
-N * 2^24-point MSM (point-range sharding, weak scaling): local Pippenger, NCCL all-gather of the
-192-byte partials, host fold.  The JSON line's `value` is device time per step with inputs resident
+One "step" = one 2^24-point G1 MSM on one batch of synthetic input: random scalars against a resident
+SRS of 2^24 distinct pseudo-random points generated on the device, with the fixed-base window table
+built once at setup (zkp_srs_precompute, the KzgScheme::new side of the seam; not in the timed region,
+exactly as the SRS upload is not).  At N > 1 every rank owns a 2^24-point shard of an N * 2^24-point
+MSM (point-range sharding, weak scaling): local Pippenger, NCCL all-gather of the 192-byte partials,
+host fold.  The JSON line's `value` is device time per step with inputs resident
 in HBM; `e2e` is the same step through the reference-facing entry point `zkp_msm_g1` with the
 scalars in pinned HOST memory (H2D copy and result read-back inside the timed region).  `extra`
 carries the other numbers BASELINE.json names (MSM 2^20, NTT 2^24) measured the same way.
@@ -35,8 +37,9 @@ LOG_N_NTT = 24
 IMAD_PER_FQ_MUL = 300       # 12-limb CIOS = 2*12^2 + 12 multiply-adds
 FQ_MUL_PER_MADD = 10        # XYZZ mixed add 8M + 2S
 IMAD_PER_FR_MUL = 136       # 8-limb CIOS = 2*8^2 + 8
-WORKLOAD = ("G1 MSM, 2^24 points per GPU (BLS12-381), random scalars < 2^254, distinct generated bases; "
-            "N GPUs = point-range shards of an N*2^24-point MSM + NCCL all-gather of partials")
+WORKLOAD = ("G1 MSM, 2^24 points per GPU (BLS12-381), random scalars < 2^254, resident SRS of distinct generated "
+            "points + fixed-base window table; N GPUs = point-range shards of an N*2^24-point MSM + NCCL "
+            "all-gather of partials")
 
 
 def peaks():
@@ -215,6 +218,10 @@ def run_engine(args) -> None:
     gen.manual_seed(0x5EED + rank)
     scalars = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device=dev, generator=gen)  # < 2^254 < r
     eng.srs_upload_dev(bases, n)  # resident SRS for the reference-facing entry point
+    t_tab = time.perf_counter()
+    eng.srs_precompute()          # fixed-base window table (setup, next to KzgScheme::new)
+    torch.cuda.synchronize()
+    t_tab = time.perf_counter() - t_tab
     host_scalars = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
     host_scalars.copy_(scalars)
     host_np = host_scalars.numpy().view(np.uint64)
@@ -227,9 +234,9 @@ def run_engine(args) -> None:
 
     def step_resident():
         if world == 1:
-            out, inf = eng.msm_dev(scalars, bases, n)
+            out, inf = eng.msm_dev(scalars, None, n)  # bases = resident SRS
         else:
-            out, inf = z.dist.msm_sharded(eng, scalars, bases, n, device=dev)
+            out, inf = z.dist.msm_sharded(eng, scalars, None, n, device=dev)
         result["resident"] = out
         launches["n"] += eng.last_launches("msm")
         for k, v in eng.last_phase_ms().items():
@@ -241,7 +248,7 @@ def run_engine(args) -> None:
         else:
             sdev = torch.empty_like(scalars)
             sdev.copy_(host_scalars, non_blocking=True)
-            out, inf = z.dist.msm_sharded(eng, sdev, bases, n, device=dev)
+            out, inf = z.dist.msm_sharded(eng, sdev, None, n, device=dev)
         result["e2e"] = out
 
     # warm-up also sizes every scratch buffer
@@ -266,7 +273,9 @@ def run_engine(args) -> None:
     if rank == 0:
         # ---- the other numbers BASELINE.json names, N = 1 semantics on rank 0's GPU ----
         n20 = 1 << 20
-        extra["g1_msm_2p20_ms"] = timed_local(torch, lambda: eng.msm_dev(scalars, bases, n20), 5, 3)
+        extra["g1_msm_2p24_srs_table_build_s"] = t_tab
+        extra["g1_msm_2p24_adhoc_bases_ms"] = timed_local(torch, lambda: eng.msm_dev(scalars, bases, n), 3, 1)
+        extra["g1_msm_2p20_adhoc_bases_ms"] = timed_local(torch, lambda: eng.msm_dev(scalars, bases, n20), 5, 3)
         nt = 1 << LOG_N_NTT
         poly = torch.randint(0, 2**62, (nt * 4,), dtype=torch.int64, device=dev)
         ntt_ms = timed_local(torch, lambda: eng.ntt_dev(poly, LOG_N_NTT), 10, 3)
@@ -289,7 +298,10 @@ def run_engine(args) -> None:
             "integer_bound_note": "butterfly arithmetic = N/2*log2(N)*136 IMAD; fraction of the measured IMAD.WIDE peak below",
             "int_pipe_frac": ntt_imad / (ntt_ms * 1e-3) / imad_wide if imad_wide else None,
         }
-        del poly
+        del poly, hp
+        # ---- SRS of 2^20 + 3 points: the 2^20 commitment and the end-to-end PLONK prove (config 4) ----
+        if world == 1:
+            extra.update(plonk_and_2p20(z, eng, torch, scalars))
 
     if rank != 0:
         if world > 1:
@@ -311,11 +323,13 @@ def run_engine(args) -> None:
         "algorithmic_imad_per_launch": alg_imad, "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms,
         "window_bits": c_bits, "windows": n_win, "traffic": traffic, "phases_ms": phases,
     }
-    ref_ms, ref_dt, ref_n = cpu_reference_sample(12)
-    cpu = {"value": ref_ms, "unit": "ms", "cores": 1, "kind": "port",
-           "sample": "evaluate_in_s restated (oracle/zkp_oracle.c:orc_msm_naive) on 2^12 terms = %.2f s, scaled x2^12 to 2^24; "
-                     "single-threaded like the reference" % ref_dt,
-           "best_effort_all_cores": cpu_best_effort(20)}
+    cpu = None
+    if world == 1:  # the CPU baseline is an N = 1 measurement (torchrun pins OMP_NUM_THREADS = 1)
+        ref_ms, ref_dt, ref_n = cpu_reference_sample(12)
+        cpu = {"value": ref_ms, "unit": "ms", "cores": 1, "kind": "port",
+               "sample": "evaluate_in_s restated (oracle/zkp_oracle.c:orc_msm_naive) on 2^12 terms = %.2f s, scaled x2^12 to "
+                         "2^24; single-threaded like the reference" % ref_dt,
+               "best_effort_all_cores": cpu_best_effort(20)}
     line = {
         "metric": "g1_msm_2p24_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -335,6 +349,33 @@ def run_engine(args) -> None:
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def plonk_and_2p20(z, eng, torch, scalars):
+    """BASELINE.json config 4 on this GPU: synthetic chain circuit of 2^20 - 3 gates, SRS from a fixed secret with
+    its window table, fixed blinding; wall clock inside zkp_plonk_prove (all rounds, transcript included)."""
+    import hashlib
+
+    k = 20
+    n = 1 << k
+    secret = 0x1F2E3D4C5B6A79881234567
+    blind = [(0xABCDEF0123456789 * (i + 3) ** 7) % z.FR_MODULUS for i in range(9)]
+    eng.srs_generate(secret, n + 3, want_points=False)
+    eng.srs_precompute()
+    out = {"g1_msm_2p20_ms": timed_local(torch, lambda: eng.msm_dev(scalars, None, n), 5, 3)}
+    cc = z.plonk.chain_circuit(n - 3, seed=k).compile(eng)
+    runs = []
+    digest = None
+    for _ in range(4):
+        p = z.plonk.generate_proof(cc, blind)
+        runs.append(p.timings_ms["total"])
+        digest = hashlib.sha256(p.to_bytes()).hexdigest()
+    cc.close()
+    out["plonk_prove_2p20_ms"] = min(runs[1:])
+    out["plonk_prove_2p20_runs_ms"] = runs
+    out["plonk_proof_sha256"] = digest
+    out["plonk_config"] = "chain circuit, 2^20 - 3 gates (alternating mul / add, c_i wired to a_(i+1)), seed 20, fixed b1..b9"
+    return out
 
 
 def timed_local(torch, fn, steps, warmup):

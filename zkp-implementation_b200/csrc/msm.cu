@@ -250,7 +250,7 @@ struct RedLevels {
   uint32_t off[MAX_RED_LEVELS];  // element offset of X^l (layout [set][m_l])
   uint32_t m[MAX_RED_LEVELS];    // entries per set at level l
 };
-static constexpr uint32_t SUM_CHUNKS = 64;
+static constexpr uint32_t SUM_CHUNKS = 2048;  // stage-1 blocks per (level, set) for the largest level
 
 __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
                                                                     uint32_t nsets, G1Xyzz* __restrict__ out) {
@@ -282,6 +282,30 @@ __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz
     __syncthreads();
   }
   if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz(&sh[0]));
+}
+
+// stage 2: A[y] = sum of the stage-1 partials of (level, set) y (layout [y][chunks])
+__global__ void __launch_bounds__(RED_THREADS) msm_plane_sum2_kernel(const G1Xyzz* __restrict__ part, uint32_t chunks,
+                                                                     G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[RED_THREADS];
+  const uint32_t tid = threadIdx.x;
+  const G1Xyzz* in = part + (size_t)blockIdx.x * chunks;
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (uint32_t i = tid; i < chunks; i += blockDim.x) {
+    G1Xyzz p = ld_xyzz(in + i);
+    xyzz_add(acc, p);
+  }
+  st_xyzz(&sh[tid], acc);
+  __syncthreads();
+  for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
+      xyzz_add(a, b);
+      st_xyzz(&sh[tid], a);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) st_xyzz(out + blockIdx.x, ld_xyzz(&sh[0]));
 }
 
 // F[w] = G[w] + sum_l 2^l A_l[w]: one block per set, thread l doubles (sum of its plane's chunk sums) l times,
@@ -488,7 +512,10 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
-  ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + (size_t)SUM_CHUNKS * MAX_RED_LEVELS * nsets) * sizeof(G1Xyzz)));
+  uint32_t chunks = ((nbuckets >> 1) + 2 * RED_THREADS - 1) / (2 * RED_THREADS);
+  if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + ((size_t)chunks + 1) * (c - 1) * nsets) * sizeof(G1Xyzz)));
   ZKP_TRY(m.win_out.reserve((size_t)(nsets + 1) * sizeof(G1Xyzz)));
   uint32_t* keys_a = m.keys_a.as<uint32_t>();
   uint32_t* keys_b = m.keys_b.as<uint32_t>();
@@ -586,17 +613,14 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
       off += (size_t)mm * nsets;
     }
     // A_l = sum of the odd entries of X^l, every level and set in one launch; the combine finishes the sums
-    uint32_t chunks = ((nbuckets >> 1) + 2 * RED_THREADS - 1) / (2 * RED_THREADS);
-    if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
-    if (chunks < 1) chunks = 1;
-    if (levels) {
-      ZKP_LAUNCH(msm_plane_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
-                 nsets, sum_scratch);
-      ctx->msm_launches++;
-    }
-    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3(nsets), dim3(32), 0, st, (const G1Xyzz*)sum_scratch, chunks,
+    G1Xyzz* plane = sum_scratch + (size_t)chunks * levels * nsets;  // [levels * nsets]
+    ZKP_LAUNCH(msm_plane_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
+               nsets, sum_scratch);
+    ZKP_LAUNCH(msm_plane_sum2_kernel, dim3(levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)sum_scratch, chunks,
+               plane);
+    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3(nsets), dim3(32), 0, st, (const G1Xyzz*)plane, 1u,
                (const G1Xyzz*)(lvl_buf + off), levels, nsets, win_out);
-    ctx->msm_launches++;
+    ctx->msm_launches += 3;
   }
   phase_mark(ctx, 5);
   ZKP_TRY(rt::check_last());
