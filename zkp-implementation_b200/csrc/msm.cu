@@ -250,7 +250,8 @@ struct RedLevels {
   uint32_t off[MAX_RED_LEVELS];  // element offset of X^l (layout [set][m_l])
   uint32_t m[MAX_RED_LEVELS];    // entries per set at level l
 };
-static constexpr uint32_t SUM_CHUNKS = 2048;  // stage-1 blocks per (level, set) for the largest level
+static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (level, set) for the largest level
+static constexpr uint32_t SUM_MIN_CHUNK = 16 * RED_THREADS;  // >= 16 serial additions per thread ahead of the 7-step tree
 
 __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
                                                                     uint32_t nsets, G1Xyzz* __restrict__ out) {
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz
   const uint32_t l = blockIdx.y / nsets, w = blockIdx.y - l * nsets, tid = threadIdx.x;
   const uint32_t count = lv.m[l] >> 1;  // odd entries
   uint32_t chunk = (count + gridDim.x - 1) / gridDim.x;
-  if (chunk < 2 * RED_THREADS) chunk = 2 * RED_THREADS;  // short arrays: fewer, fuller blocks
+  if (chunk < SUM_MIN_CHUNK) chunk = SUM_MIN_CHUNK;  // short arrays: fewer, fuller blocks
   const uint32_t lo = blockIdx.x * chunk;
   if (lo >= count) {  // block-uniform: nothing to sum
     if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, G1Xyzz::infinity());
@@ -512,7 +513,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
-  uint32_t chunks = ((nbuckets >> 1) + 2 * RED_THREADS - 1) / (2 * RED_THREADS);
+  uint32_t chunks = ((nbuckets >> 1) + SUM_MIN_CHUNK - 1) / SUM_MIN_CHUNK;
   if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
   if (chunks < 1) chunks = 1;
   ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + ((size_t)chunks + 1) * (c - 1) * nsets) * sizeof(G1Xyzz)));
