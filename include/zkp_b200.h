@@ -115,6 +115,13 @@ int zkp_poly_mul_fr(zkp_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* 
 /* a[i] *= b[i] on device vectors (the pointwise step of a product kept resident). */
 int zkp_fr_mul_pointwise_dev(zkp_ctx* ctx, void* a_dev, const void* b_dev, size_t n);
 
+/* ---- `KzgScheme::open` / `open_vector` (kzg/src/scheme.rs:108-120, 132-142): y = p(z), witness = commit((p - y) / (X - z))
+ *      against the resident SRS.  coeffs: n x 4 u64 (trailing zeros are trimmed as DensePolynomial does); an empty
+ *      polynomial returns ZKP_B200_ERR_EMPTY_POLY (scheme.rs:112 expect("at least 1")).  Evaluation, division and the
+ *      commitment all run on the device. ------------------------------------------------------------------------- */
+int zkp_kzg_open(zkp_ctx* ctx, const uint64_t* coeffs, size_t n, const uint64_t z[4], uint64_t out_xy[12],
+                 uint8_t* out_infinity, uint64_t out_y[4]);
+
 /* ---- multi-GPU four-step NTT (one process per GPU).  N = 2^r x 2^(log_n - r),
  *      r = zkp_ntt_dist_rows_log.  Rank g of G holds
  *        layout A:  a[j1][c]  = x[j1 * 2^(log_n-r) + g * 2^(log_n-r)/G + c]   (its column block, row-major)

@@ -89,3 +89,25 @@ def test_srs_generation_matches_oracle(zkp, engine, coracle):
     secret = 0xDEADBEEFCAFE
     srs = zkp.Srs.new_from_secret(engine, secret, 70)
     assert (srs.g1_limbs() == coracle.srs(F.fr_to_mont_array([secret]), 73)).all()
+
+
+def test_open_on_device_vs_oracle(zkp, engine, coracle, pyref):
+    """scheme.rs:108-120 at a size where the device path's multi-block scans / evaluation are exercised:
+    (witness, y) equal the oracle's Horner + synthetic division + MSM; z = 0 and a constant polynomial too."""
+    F = zkp.fields
+    n = 3000
+    srs = zkp.Srs.new_from_secret(engine, 0x4242, n)
+    scheme = zkp.KzgScheme(engine, srs)
+    rng = pyref.SplitMix64(91)
+    poly = [rng.fr() for _ in range(n)] + [0, 0]  # trailing zeros are trimmed like DensePolynomial does
+    pts = srs.g1_limbs()
+    for z in (rng.fr(), 0, 1):
+        op = scheme.open(poly, z)
+        q, y = coracle.open_quotient(F.fr_to_mont_array(poly[:n]), F.fr_to_mont_array([z]))
+        assert op.evaluation == F.fr_from_mont_array(y)[0] == pyref.poly_eval(poly, z)
+        want = coracle.msm_pippenger(q, pts[: q.shape[0]])
+        assert op.point == F.g1_from_array(want)[0]
+    const = scheme.open([5], 9)
+    assert const.evaluation == 5 and const.point is None  # quotient of a constant is the zero polynomial
+    with pytest.raises(ValueError, match="at least 1"):
+        scheme.open([0, 0], 3)

@@ -56,6 +56,8 @@ ABI = {
     "zkp_poly_mul_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_fr_mul_pointwise_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "zkp_kzg_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_ntt_dist_rows_log": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     "zkp_ntt_dist_stage_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                                               ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
@@ -231,6 +233,17 @@ class Engine:
         self._check(self.lib.zkp_msm_g1_multi_dev(self._h, k, ctypes.cast(ptrs, ctypes.c_void_p),
                                                   ctypes.cast(ln, ctypes.c_void_p), _ptr(out), _ptr(inf)))
         return [(out[j], bool(inf[j])) for j in range(k)]
+
+    def kzg_open(self, coeffs: np.ndarray, z: int):
+        """`KzgScheme::open` on the device: (witness xy limbs, infinity flag, evaluation as a canonical int)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        za = fields.fr_to_mont_array([z])
+        out = np.zeros(12, dtype=np.uint64)
+        y = np.zeros((1, 4), dtype=np.uint64)
+        inf = ctypes.c_uint8(0)
+        self._check(self.lib.zkp_kzg_open(self._h, _ptr(coeffs), coeffs.shape[0], _ptr(za), _ptr(out), ctypes.byref(inf),
+                                          _ptr(y)))
+        return out, bool(inf.value), fields.fr_from_mont_array(y)[0]
 
     def msm_partial_dev(self, scalars_dev, bases_dev, n: int) -> np.ndarray:
         out = np.zeros(24, dtype=np.uint64)

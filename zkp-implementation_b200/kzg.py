@@ -21,8 +21,8 @@ reference (kzg/src)                    here
 and are not rebuilt.  Polynomials are coefficient lists of Python ints (canonical Fr values), low
 degree first, as `DensePolynomial::coeffs`.
 
-The O(n) scalar work of `open` (Horner evaluation and the synthetic division by X - z) is host
-arithmetic in the reference too (scheme.rs:110-117); the G1 sums all go through the GPU MSM.
+`open` runs entirely on the device (zkp_kzg_open: chunked Horner, division by X - z as a weighted suffix
+scan, commitment of the quotient); no field or group arithmetic lives in this file.
 """
 from __future__ import annotations
 
@@ -126,24 +126,14 @@ class KzgScheme:
         out, inf = self.engine.msm(scalars)
         return KzgCommitment(None if inf else fields.g1_from_array(out)[0])
 
-    @staticmethod
-    def _quotient(coeffs: List[int], z: int) -> Tuple[List[int], int]:
-        """scheme.rs:110-117: y = p(z); q = (p - y) / (X - z)."""
+    def open(self, polynomial: Sequence[int], z: int) -> KzgOpening:
+        """scheme.rs:108-120: evaluation, division by (X - z) and the commitment of the quotient all on the device
+        (zkp_kzg_open)."""
+        coeffs = _trim(polynomial)
         if not coeffs:
             raise ValueError("at least 1")  # scheme.rs:112 expect("at least 1")
-        n = len(coeffs)
-        q = [0] * (n - 1)
-        carry = 0
-        for i in range(n - 1, 0, -1):
-            carry = (coeffs[i] + carry * z) % FR_MODULUS
-            q[i - 1] = carry
-        y = (coeffs[0] + carry * z) % FR_MODULUS
-        return _trim(q), y
-
-    def open(self, polynomial: Sequence[int], z: int) -> KzgOpening:
-        """scheme.rs:108-120."""
-        q, y = self._quotient(_trim(polynomial), int(z) % FR_MODULUS)
-        return KzgOpening(self._evaluate_in_s(q), y)
+        out, inf, y = self.engine.kzg_open(fields.fr_to_mont_array(coeffs), int(z) % FR_MODULUS)
+        return KzgOpening(None if inf else fields.g1_from_array(out)[0], y)
 
     def open_vector(self, coeffs: Sequence[int], z: int) -> KzgOpening:
         """scheme.rs:132-142."""
