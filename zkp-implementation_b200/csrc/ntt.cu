@@ -23,9 +23,15 @@ namespace zkp {
 
 static constexpr uint32_t WLOG = 11;       // sub-transform twiddle table: omega_{2^11}^i, i < 2^10
 static constexpr uint32_t RMAX = 9;        // largest digit of a multi-pass schedule
-static constexpr uint32_t TILE_LOG = 11;   // elements per shared-memory tile (64 KB)
-static constexpr uint32_t SINGLE_MAX = 11; // largest transform done in one tile
-static constexpr uint32_t NTT_THREADS = 256;
+#ifndef NTT_TILE_LOG
+#define NTT_TILE_LOG 11
+#endif
+#ifndef NTT_THREADS_PER_CTA
+#define NTT_THREADS_PER_CTA 256
+#endif
+static constexpr uint32_t TILE_LOG = NTT_TILE_LOG;   // elements per shared-memory tile (2^11 = 64 KB)
+static constexpr uint32_t SINGLE_MAX = NTT_TILE_LOG; // largest transform done in one tile
+static constexpr uint32_t NTT_THREADS = NTT_THREADS_PER_CTA;
 #ifndef NTT_MIN_BLOCKS
 #define NTT_MIN_BLOCKS 2
 #endif
