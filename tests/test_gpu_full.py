@@ -128,3 +128,54 @@ def test_e2e_host_buffers(zkp, gpu_engine, coracle):
     d = a.copy()
     gpu_engine.ntt(d, 18)
     assert (d == coracle.ntt(a, 18)).all()
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_fixed_base_vs_oracle(zkp, gpu_engine, coracle, log_n):
+    """The path every kzg commit takes: resident SRS + window table (zkp_srs_precompute), full compare with the
+    oracle, and a batch of three commitments as one pipeline (zkp_msm_g1_multi_dev)."""
+    import torch
+
+    F = zkp.fields
+    n = 1 << log_n
+    bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
+    gpu_engine.generate_bases_dev(0x9000 + log_n, n, bases)
+    gpu_engine.srs_upload_dev(bases, n)
+    gpu_engine.srs_precompute()
+    hb = _host(bases, 12)
+    vecs = [F.random_fr_mont(0xA000 + log_n + j, n - 3 * j) for j in range(3)]
+    out, inf = gpu_engine.msm_dev(_dev(vecs[0]), None, n)
+    want0 = coracle.msm_pippenger(vecs[0], hb)
+    assert (out == want0).all() and not inf
+    dv = [_dev(v) for v in vecs]
+    got = gpu_engine.msm_multi_dev(dv, [v.shape[0] for v in vecs])
+    for j, (o, i) in enumerate(got):
+        assert (o == coracle.msm_pippenger(vecs[j], hb[:vecs[j].shape[0]])).all() and not i, j
+    gpu_engine.srs_upload_dev(bases, 1)
+
+
+def test_msm_2p24_fixed_base_properties(zkp, gpu_engine, pyref):
+    """2^24 points through the fixed-base table (the bench's step): closed-form sum with equal scalars, and random
+    scalars equal to the windowed path over the same points (two different bucket layouts, same group element)."""
+    import torch
+
+    F = zkp.fields
+    n = 1 << 24
+    seed = 0x2425
+    bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
+    gpu_engine.generate_bases_dev(seed, n, bases)
+    gpu_engine.srs_upload_dev(bases, n)
+    gpu_engine.srs_precompute()
+    a0, dl = _progression(seed)
+    k = pyref.R - 0x1234567  # large scalar: every window non-trivial, negative digits
+    s = _dev(np.repeat(F.fr_to_mont_array([k]), n, axis=0))
+    out, inf = gpu_engine.msm_dev(s, None, n)
+    exp = pyref.g1_mul(pyref.G1, k * (n * a0 + dl * (n * (n - 1) // 2)) % pyref.R)
+    assert F.g1_from_array(out)[0] == exp and not inf
+    del s
+    sr = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device="cuda")
+    fixed, _ = gpu_engine.msm_dev(sr, None, n)
+    assert gpu_engine.last_msm_shape()[0] >= 20
+    windowed, _ = gpu_engine.msm_dev(sr, bases, n)
+    assert (fixed == windowed).all()
+    gpu_engine.srs_upload_dev(bases, 1)  # drop the 18 GiB table
