@@ -77,6 +77,8 @@ int zkp_srs_precompute(zkp_ctx* ctx, uint32_t window_bits);
 /* `Srs::new_from_secret` (kzg/src/srs.rs:48-69): fill the resident SRS with [secret^i * G], i < n,
  * computed on the GPU; optionally copy the points back to `xy_out` (n x 12 u64, may be NULL). */
 int zkp_srs_generate(zkp_ctx* ctx, const uint64_t secret[4], size_t n, uint64_t* xy_out);
+/* The point range [first, first + n) of that SRS: the shard of one rank of a point-range-sharded SRS. */
+int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t secret[4], size_t first, size_t n, uint64_t* xy_out);
 
 /* ---- MSM: replaces `KzgScheme::evaluate_in_s` (kzg/src/scheme.rs:84-96) ---------------------
  * out = sum_{i<n} scalars[i] * srs[i], normalised affine; n == 0 -> infinity (scheme.rs:94).
@@ -94,6 +96,10 @@ int zkp_msm_g1_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev,
  * MSM of the batch is one more bucket set of the same sort / accumulate / reduce launches.  out_xy: count x 12. */
 int zkp_msm_g1_multi_dev(zkp_ctx* ctx, uint32_t count, const void* const* scalars_dev, const size_t* lens, uint64_t* out_xy,
                          uint8_t* out_infinity /* count, or NULL */);
+/* The same batch as un-normalised partial sums (count x 24 u64, XYZZ) over this rank's SRS shard: the sharded prover
+ * all-gathers them and folds per commitment with zkp_g1_fold_partials. */
+int zkp_msm_g1_multi_partial_dev(zkp_ctx* ctx, uint32_t count, const void* const* scalars_dev, const size_t* lens,
+                                 uint64_t* out_xyzz);
 /* Multi-GPU point-range sharding: each rank computes the un-normalised partial sum of its shard
  * (XYZZ coordinates, 4 x 6 u64) ...                                                              */
 int zkp_msm_g1_partial_dev(zkp_ctx* ctx, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xyzz[24]);

@@ -71,6 +71,17 @@ int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* o
 int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
                     double* timings_ms);
 
+/* The same proof with the nine commitments point-range-sharded over `world` GPUs, one process each:
+ * the SRS resident in `ctx` is [srs_first, srs_first + zkp_srs_len) of the global SRS of `srs_total` points
+ * (zkp_srs_generate_range / zkp_srs_upload of the shard, then zkp_srs_precompute); every rank runs the whole prover
+ * -- the transforms and pointwise kernels are a small part of a proof -- but only its range of each MSM, and the
+ * 192-byte partial sums go through `allgather` (recv = world x bytes, rank-major; NCCL / gloo behind it) and are
+ * folded on every rank.  All ranks return the same proof, byte-identical to zkp_plonk_prove's. */
+typedef int (*zkp_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
+int zkp_plonk_prove_sharded(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                            double* timings_ms, uint32_t rank, uint32_t world, size_t srs_first, size_t srs_total,
+                            zkp_allgather_fn allgather, void* user);
+
 /* Same proof, computed the way prover.rs is written: every `&a * &b` of compute_quotient_polynomial as its own
  * GPU product (zkp_poly_mul_fr: 2 NTT + pointwise + iNTT at 4n / 8n), polynomials held on the host between
  * calls.  Kept as an independent cross-check of zkp_plonk_prove (the proofs must be byte-identical). */

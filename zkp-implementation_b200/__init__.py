@@ -46,6 +46,10 @@ ABI = {
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_msm_g1_multi_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_msm_g1_multi_partial_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p]),
+    "zkp_srs_generate_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                              ctypes.c_void_p]),
     "zkp_msm_g1_partial_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                               ctypes.c_void_p]),
     "zkp_g1_fold_partials": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
@@ -193,10 +197,11 @@ class Engine:
     def srs_len(self) -> int:
         return int(self.lib.zkp_srs_len(self._h))
 
-    def srs_generate(self, secret: int, n: int, want_points: bool = True) -> Optional[np.ndarray]:
+    def srs_generate(self, secret: int, n: int, want_points: bool = True, first: int = 0) -> Optional[np.ndarray]:
+        """Resident SRS = [secret^i G] for i in [first, first + n) (first > 0: one rank's shard of a sharded SRS)."""
         sec = fields.fr_to_mont_array([secret])
         out = np.zeros((n, 12), dtype=np.uint64) if want_points else None
-        self._check(self.lib.zkp_srs_generate(self._h, _ptr(sec), n, _ptr(out)))
+        self._check(self.lib.zkp_srs_generate_range(self._h, _ptr(sec), first, n, _ptr(out)))
         return out
 
     # -- MSM --------------------------------------------------------------------------------------

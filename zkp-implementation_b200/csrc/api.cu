@@ -17,7 +17,7 @@ struct zkp_ctx {
 
 namespace zkp {
 int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out);
-int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t n, G1Affine* out);
+int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t start, size_t n, G1Affine* out);
 int bench_imad(Ctx* ctx, double* wide, double* lo);
 }  // namespace zkp
 
@@ -173,13 +173,17 @@ int zkp_srs_precompute(zkp_ctx* h, uint32_t window_bits) {
 }
 
 int zkp_srs_generate(zkp_ctx* h, const uint64_t secret[4], size_t n, uint64_t* xy_out) {
+  return zkp_srs_generate_range(h, secret, 0, n, xy_out);
+}
+
+int zkp_srs_generate_range(zkp_ctx* h, const uint64_t secret[4], size_t first, size_t n, uint64_t* xy_out) {
   if (!h || !secret) return ZKP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   ZKP_TRY(srs_alloc(&h->c, n));
   Fr s;
   memcpy(s.v, secret, 32);
-  ZKP_TRY(gen_srs_dev(&h->c, s, n, h->c.srs));
+  ZKP_TRY(gen_srs_dev(&h->c, s, first, n, h->c.srs));
   if (xy_out) ZKP_TRY(rt::d2h(xy_out, h->c.srs, n * sizeof(G1Affine), h->c.stream));
   return rt::sync(h->c.stream);
 }
@@ -242,6 +246,33 @@ int zkp_msm_g1_multi_dev(zkp_ctx* h, uint32_t count, const void* const* scalars_
     c->msm_launches = launches;
   }
   for (uint32_t j = 0; j < count; j++) write_affine(acc[j], out_xy + 12 * j, out_infinity ? out_infinity + j : nullptr);
+  return ZKP_OK;
+}
+
+int zkp_msm_g1_multi_partial_dev(zkp_ctx* h, uint32_t count, const void* const* scalars_dev, const size_t* lens,
+                                 uint64_t* out_xyzz) {
+  if (!h || (count && (!scalars_dev || !lens || !out_xyzz)) || count > 16) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  Ctx* c = &h->c;
+  ZKP_TRY(rt::set_device(c->device));
+  size_t shortest = (size_t)-1;
+  for (uint32_t j = 0; j < count; j++) {
+    if (lens[j] > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
+    if (lens[j] && !scalars_dev[j]) return ZKP_ERR_INVALID_ARG;
+    if (lens[j] < shortest) shortest = lens[j];
+  }
+  G1Xyzz acc[16];
+  if (count > 1 && c->srs_tab && shortest >= c->srs_len / 4) {
+    ZKP_TRY(msm_run_multi_dev(c, (const Fr* const*)scalars_dev, lens, count, c->srs_tab, acc, c->srs_tab_c, c->srs_len));
+  } else {
+    uint32_t launches = 0;
+    for (uint32_t j = 0; j < count; j++) {
+      ZKP_TRY(msm_nolock(c, scalars_dev[j], nullptr, lens[j], &acc[j]));
+      launches += c->msm_launches;
+    }
+    c->msm_launches = launches;
+  }
+  memcpy(out_xyzz, acc, (size_t)count * sizeof(G1Xyzz));
   return ZKP_OK;
 }
 

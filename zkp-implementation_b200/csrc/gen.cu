@@ -35,11 +35,12 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_chain_kernel(const G1Xyzz* st
 }
 
 // tmp[i] = secret^i * G (XYZZ): MSB-first double-and-add over the canonical power, as ark-ec does
-__global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t n, G1Xyzz* tmp) {
+// (`start`: index of the first power, for a rank that owns a point range of a sharded SRS)
+__global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t start, size_t n, G1Xyzz* tmp) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t first = t * SRS_RUN;
   if (first >= n) return;
-  Fr cur = fp_pow_u64(secret, (uint64_t)first);
+  Fr cur = fp_pow_u64(secret, (uint64_t)(start + first));
   const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
   for (uint32_t i = 0; i < SRS_RUN && first + i < n; i++) {
     Fr k = fp_from_mont(cur);
@@ -127,13 +128,13 @@ int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
   return st;
 }
 
-int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t n, G1Affine* out) {
+int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t start, size_t n, G1Affine* out) {
   if (n == 0) return ZKP_OK;
   DevBuf tmp;
   ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
   const size_t threads = (n + SRS_RUN - 1) / SRS_RUN;
   ZKP_LAUNCH(gen_srs_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
-             ctx->stream, secret, n, tmp.as<G1Xyzz>());
+             ctx->stream, secret, start, n, tmp.as<G1Xyzz>());
   int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
   if (st == ZKP_OK) st = rt::sync(ctx->stream);
   tmp.release();

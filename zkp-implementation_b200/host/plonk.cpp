@@ -529,6 +529,18 @@ struct DevTimers {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 };
 
+// Point-range sharding of the commitments over several GPUs (one process each): the SRS resident in this rank's
+// context is [first, first + zkp_srs_len) of the global SRS; every rank runs the whole prover (the transforms and
+// pointwise work are a small part of a proof) but only its range of each commitment, and the 192-byte partial sums
+// are exchanged through `allgather` (NCCL in production, gloo in the CPU tests) and folded.
+struct Shard {
+  uint32_t rank = 0, world = 1;
+  size_t first = 0, total = 0;  // this rank's first global SRS index; global SRS length
+  zkp_allgather_fn allgather = nullptr;
+  void* user = nullptr;
+  bool on() const { return world > 1; }
+};
+
 // Workspace layout inside cc->d_work (element offsets); L = n + 4 slots per coefficient vector.
 struct Work {
   size_t n, d, L;
@@ -546,20 +558,39 @@ struct Work {
   static size_t elems(size_t n, size_t d) { return 11 * (n + 4) + 5 * d; }
 };
 
-int dev_commit(zkp_ctx* ctx, const Fr* scalars_dev, size_t len, G1& out, DevTimers& tm) {
+// several commitments against the resident SRS as one MSM pipeline (zkp_msm_g1_multi_dev); sharded: this rank's
+// range of every polynomial, all-gather of the partial sums, fold
+int dev_commit_multi(zkp_ctx* ctx, const Shard& sh, uint32_t count, const Fr* const* scalars_dev, const size_t* lens, G1* out,
+                     DevTimers& tm) {
   auto t = std::chrono::steady_clock::now();
-  uint8_t inf = 0;
-  int st = zkp_msm_g1_dev(ctx, scalars_dev, nullptr, len, out.xy, &inf);  // bases = resident SRS
+  int st = 0;
+  if (!sh.on()) {
+    st = zkp_msm_g1_multi_dev(ctx, count, (const void* const*)scalars_dev, lens, out[0].xy, nullptr);
+  } else {
+    const size_t mine = zkp_srs_len(ctx);
+    const void* ptrs[16];
+    size_t part_len[16];
+    for (uint32_t j = 0; j < count; j++) {
+      const size_t hi = std::min(lens[j], sh.first + mine);
+      part_len[j] = hi > sh.first ? hi - sh.first : 0;
+      ptrs[j] = scalars_dev[j] + sh.first;
+    }
+    std::vector<uint64_t> part((size_t)count * 24), all((size_t)count * 24 * sh.world);
+    st = zkp_msm_g1_multi_partial_dev(ctx, count, ptrs, part_len, part.data());
+    if (!st) st = sh.allgather(sh.user, part.data(), part.size() * 8, all.data());
+    std::vector<uint64_t> mine_of(24 * (size_t)sh.world);
+    for (uint32_t j = 0; j < count && !st; j++) {
+      for (uint32_t g = 0; g < sh.world; g++)
+        memcpy(&mine_of[24 * g], &all[((size_t)g * count + j) * 24], 192);
+      uint8_t inf = 0;
+      st = zkp_g1_fold_partials(mine_of.data(), sh.world, out[j].xy, &inf);
+    }
+  }
   tm.msm += Timers::since(t);
   return st;
 }
-
-// several commitments against the resident SRS as one MSM pipeline (zkp_msm_g1_multi_dev)
-int dev_commit_multi(zkp_ctx* ctx, uint32_t count, const Fr* const* scalars_dev, const size_t* lens, G1* out, DevTimers& tm) {
-  auto t = std::chrono::steady_clock::now();
-  int st = zkp_msm_g1_multi_dev(ctx, count, (const void* const*)scalars_dev, lens, out[0].xy, nullptr);
-  tm.msm += Timers::since(t);
-  return st;
+int dev_commit(zkp_ctx* ctx, const Shard& sh, const Fr* scalars_dev, size_t len, G1& out, DevTimers& tm) {
+  return dev_commit_multi(ctx, sh, 1, &scalars_dev, &len, &out, tm);
 }
 
 // (poly - poly(root)) / (X - root) in place on the device: weight by root^i, suffix sums, unweight.
@@ -580,15 +611,38 @@ int dev_divide_linear(zkp_ctx* ctx, const Work& w, Fr* data, size_t len, const F
 
 }  // namespace
 
+static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_t* blinding, zkp_plonk_proof* out,
+                        double* timings_ms, const Shard& sh);
+
 int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_t* blinding, zkp_plonk_proof* out,
                     double* timings_ms) {
+  return prove_device(ctx, cc_in, blinding, out, timings_ms, Shard());
+}
+
+int zkp_plonk_prove_sharded(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                            double* timings_ms, uint32_t rank, uint32_t world, size_t srs_first, size_t srs_total,
+                            zkp_allgather_fn allgather, void* user) {
+  if (world == 0 || rank >= world || (world > 1 && !allgather)) return ZKP_B200_ERR_INVALID_ARG;
+  Shard sh;
+  sh.rank = rank;
+  sh.world = world;
+  sh.first = srs_first;
+  sh.total = srs_total;
+  sh.allgather = allgather;
+  sh.user = user;
+  return prove_device(ctx, cc, blinding, out, timings_ms, sh);
+}
+
+static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_t* blinding, zkp_plonk_proof* out,
+                        double* timings_ms, const Shard& sh) {
   if (!ctx || !cc_in || !blinding || !out || cc_in->ctx != ctx) return ZKP_B200_ERR_INVALID_ARG;
   zkp_plonk_compiled* cc = const_cast<zkp_plonk_compiled*>(cc_in);  // the workspace is a cache, not circuit state
   DevTimers tm;
   const size_t n = cc->size, d = cc->d;
   const uint32_t log_n = cc->log_n;
   const Fr w = cc->omega, one = Fr::one();
-  if (zkp_srs_len(ctx) < n + 3) return ZKP_B200_ERR_SRS_TOO_SMALL;  // scheme.rs:86 for the degree n + 2 commitment
+  if ((sh.on() ? sh.total : zkp_srs_len(ctx)) < n + 3) return ZKP_B200_ERR_SRS_TOO_SMALL;  // scheme.rs:86 for the degree n + 2 commitment
+  if (sh.on() && sh.first + zkp_srs_len(ctx) > sh.total) return ZKP_B200_ERR_INVALID_ARG;
   if (!cc->d_work) {
     cc->work_elems = Work::elems(n, d);
     PLONK_TRY(zkp_dev_alloc(ctx, cc->work_elems * 32, (void**)&cc->d_work));
@@ -611,7 +665,7 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
   {
     const Fr* polys[3] = {wk.coef(0), wk.coef(1), wk.coef(2)};
     const size_t lens[3] = {n + 2, n + 2, n + 2};
-    PLONK_TRY(dev_commit_multi(ctx, 3, polys, lens, &cm[0], tm));  // commit_round1 (prover.rs:571-581)
+    PLONK_TRY(dev_commit_multi(ctx, sh, 3, polys, lens, &cm[0], tm));  // commit_round1 (prover.rs:571-581)
   }
 
   // ---- Round 2 (prover.rs:98-123, 302-377) ----
@@ -649,7 +703,7 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
     const Fr vals[6] = {-b[9], -b[8], -b[7], b[9], b[8], b[7]};
     PLONK_TRY(zkp_fr_add_at_dev(ctx, wk.coef(3), 6, idx, vals[0].v));
   }
-  PLONK_TRY(dev_commit(ctx, wk.coef(3), n + 3, cm[3], tm));
+  PLONK_TRY(dev_commit(ctx, sh, wk.coef(3), n + 3, cm[3], tm));
 
   // ---- Round 3 (prover.rs:136-150, 381-444) ----
   ch.feed(cm[3]);
@@ -702,7 +756,7 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
       slice_len[i] = hi - lo;
       polys[i] = wk.t() + lo;
     }
-    PLONK_TRY(dev_commit_multi(ctx, 3, polys, slice_len, &cm[4], tm));  // SlicePoly::commit (slice_polynomial.rs:51-53)
+    PLONK_TRY(dev_commit_multi(ctx, sh, 3, polys, slice_len, &cm[4], tm));  // SlicePoly::commit (slice_polynomial.rs:51-53)
   }
   const uint64_t degree = (uint64_t)tmp - 1;
 
@@ -725,7 +779,24 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
   {
     G1 para[6];
     auto t = std::chrono::steady_clock::now();
-    PLONK_TRY(zkp_g1_mul_srs0(ctx, bars[0].v, 6, para[0].xy));  // scheme.commit_para x 6
+    if (!sh.on()) {
+      PLONK_TRY(zkp_g1_mul_srs0(ctx, bars[0].v, 6, para[0].xy));  // scheme.commit_para x 6
+    } else {  // g1_points[0] lives on the rank whose shard starts at 0; its six points are what everybody hashes
+      std::vector<uint64_t> mine(6 * 12, 0), all((size_t)6 * 12 * sh.world);
+      if (sh.first == 0) PLONK_TRY(zkp_g1_mul_srs0(ctx, bars[0].v, 6, mine.data()));
+      std::vector<uint64_t> owner_flag_and_pts(1 + 6 * 12, 0);
+      owner_flag_and_pts[0] = sh.first == 0 ? 1 : 0;
+      memcpy(&owner_flag_and_pts[1], mine.data(), 6 * 96);
+      std::vector<uint64_t> gathered((size_t)(1 + 6 * 12) * sh.world);
+      PLONK_TRY(sh.allgather(sh.user, owner_flag_and_pts.data(), owner_flag_and_pts.size() * 8, gathered.data()));
+      bool found = false;
+      for (uint32_t g = 0; g < sh.world && !found; g++)
+        if (gathered[(size_t)g * (1 + 6 * 12)] == 1) {
+          memcpy(para[0].xy, &gathered[(size_t)g * (1 + 6 * 12) + 1], 6 * 96);
+          found = true;
+        }
+      if (!found) return ZKP_B200_ERR_INVALID_ARG;
+    }
     tm.msm += Timers::since(t);
     for (int i = 0; i < 6; i++) ch.feed(para[i]);
   }
@@ -775,7 +846,7 @@ int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uint64_
     if (!rem_ok) return ZKP_PLONK_ERR_REMAINDER;  // "w_ev_wx was computed incorrectly"
     const Fr* polys[2] = {wk.wx() + 1, wk.wwx() + 1};
     const size_t lens[2] = {r_len - 1, n + 2};
-    PLONK_TRY(dev_commit_multi(ctx, 2, polys, lens, &cm[7], tm));
+    PLONK_TRY(dev_commit_multi(ctx, sh, 2, polys, lens, &cm[7], tm));
   }
   ch.feed(cm[7]); ch.feed(cm[8]);
   Fr u;

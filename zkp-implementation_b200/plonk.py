@@ -45,6 +45,8 @@ PLONK_ABI = {
     "zkp_plonk_compiled_poly": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "zkp_plonk_prove": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "zkp_plonk_prove_products": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "zkp_plonk_prove_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t,
+                                               ctypes.c_size_t, _vp, _vp]),
     "zkp_plonk_numden_dev": (ctypes.c_int, [_vp, _vp]),
     "zkp_plonk_quotient_dev": (ctypes.c_int, [_vp, _vp]),
     "zkp_plonk_gate_check_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]),
@@ -275,3 +277,43 @@ def chain_circuit(n_gates: int, seed: int) -> Circuit:
     c.add_gates_bulk(kinds, pos, fields.fr_to_mont_array(vals).reshape(n_gates, 3, 4),
                      np.zeros((n_gates, 4), dtype=np.uint64))
     return c
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+def generate_proof_sharded(compiled_circuit: CompiledCircuit, blinding: Sequence[int], rank: int, world: int,
+                           srs_first: int, srs_total: int, group=None, device=None) -> Proof:
+    """generate_proof with the commitments point-range-sharded over the ranks of a torch.distributed group
+    (zkp_plonk_prove_sharded): this rank's engine holds SRS points [srs_first, srs_first + engine.srs_len())."""
+    import torch
+    import torch.distributed as dist
+
+    eng = compiled_circuit.engine
+    _bind(eng.lib)
+
+    def _allgather(_user, send, nbytes, recv):
+        try:
+            buf = (ctypes.c_uint8 * nbytes).from_address(send)
+            t = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+            if device is not None:
+                t = t.to(device)
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t, group=group)
+            flat = torch.cat(outs).cpu().numpy().tobytes()
+            ctypes.memmove(recv, flat, nbytes * world)
+            return 0
+        except Exception:  # a failed collective must not unwind through the C frames
+            return 2
+
+    cb = ALLGATHER_FN(_allgather)
+    b = fields.fr_to_mont_array(blinding)
+    ps = _ProofStruct()
+    tm = (ctypes.c_double * 4)()
+    _raise(eng, eng.lib.zkp_plonk_prove_sharded(eng._h, compiled_circuit._h, b.ctypes.data, ctypes.addressof(ps),
+                                                ctypes.addressof(tm), rank, world, srs_first, srs_total,
+                                                ctypes.cast(cb, ctypes.c_void_p), None))
+    cm = fields.g1_from_array(np.frombuffer(bytes(ps.commitments), dtype=np.uint64).reshape(9, 12))
+    ev = fields.fr_from_mont_array(np.frombuffer(bytes(ps.evaluations), dtype=np.uint64).reshape(6, 4))
+    u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
+    return Proof(*cm, *ev, u, int(ps.degree), timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "host": tm[3]})
