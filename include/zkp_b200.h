@@ -50,6 +50,8 @@ int zkp_ctx_create(zkp_ctx** out, int device);
 void zkp_ctx_destroy(zkp_ctx* ctx);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
 int zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
+/* Block until everything queued on the context's stream has finished. */
+int zkp_ctx_synchronize(zkp_ctx* ctx);
 /* Pippenger window width in bits (0 = pick from n). */
 int zkp_ctx_set_msm_window(zkp_ctx* ctx, uint32_t bits);
 /* Kernel launches issued by the last call of the given kind (0 = MSM, 1 = NTT); kind 2 / 3 return

@@ -66,8 +66,9 @@ size_t zkp_plonk_compiled_size(const zkp_plonk_compiled* cc);
 int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* out /* size x 4 */);
 
 /* prover::generate_proof (prover.rs:61-293) against the SRS resident in `ctx` (>= size + 3 points).
- * blinding: b1..b9 (9 x 4 u64, Montgomery).  timings_ms (may be NULL): [0] total, [1] MSM calls,
- * [2] NTT / poly-product calls, [3] host arithmetic. */
+ * blinding: b1..b9 (9 x 4 u64, Montgomery).  timings_ms (may be NULL; when given, the stream is synchronised at the
+ * phase boundaries so the split is exact): [0] total, [1] commitments (MSM), [2] transforms (NTT / products),
+ * [3] the rest (pointwise kernels, scans, evaluations, transcript). */
 int zkp_plonk_prove(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
                     double* timings_ms);
 

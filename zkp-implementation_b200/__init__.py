@@ -29,6 +29,7 @@ ABI = {
     "zkp_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "zkp_ctx_destroy": (None, [ctypes.c_void_p]),
     "zkp_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "zkp_ctx_set_msm_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
     "zkp_ctx_last_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "zkp_ctx_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

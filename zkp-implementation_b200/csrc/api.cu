@@ -97,6 +97,13 @@ int zkp_ctx_set_stream(zkp_ctx* h, void* stream) {
   return ZKP_OK;
 }
 
+int zkp_ctx_synchronize(zkp_ctx* h) {
+  if (!h) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return rt::sync(h->c.stream);
+}
+
 int zkp_ctx_set_msm_window(zkp_ctx* h, uint32_t bits) {
   if (!h || (bits != 0 && (bits < 2 || bits > 22))) return ZKP_ERR_INVALID_ARG;
   h->c.msm_window_bits = bits;

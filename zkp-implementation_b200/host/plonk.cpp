@@ -526,6 +526,7 @@ namespace {
 
 struct DevTimers {
   double msm = 0, ntt = 0;
+  bool precise = false;  // the caller asked for a breakdown: synchronise at the phase boundaries
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 };
 
@@ -562,6 +563,7 @@ struct Work {
 // range of every polynomial, all-gather of the partial sums, fold
 int dev_commit_multi(zkp_ctx* ctx, const Shard& sh, uint32_t count, const Fr* const* scalars_dev, const size_t* lens, G1* out,
                      DevTimers& tm) {
+  if (tm.precise) zkp_ctx_synchronize(ctx);  // queued transform / pointwise work is not charged to the commitments
   auto t = std::chrono::steady_clock::now();
   int st = 0;
   if (!sh.on()) {
@@ -638,6 +640,7 @@ static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uin
   if (!ctx || !cc_in || !blinding || !out || cc_in->ctx != ctx) return ZKP_B200_ERR_INVALID_ARG;
   zkp_plonk_compiled* cc = const_cast<zkp_plonk_compiled*>(cc_in);  // the workspace is a cache, not circuit state
   DevTimers tm;
+  tm.precise = timings_ms != nullptr;
   const size_t n = cc->size, d = cc->d;
   const uint32_t log_n = cc->log_n;
   const Fr w = cc->omega, one = Fr::one();
@@ -696,7 +699,9 @@ static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uin
     PLONK_TRY(zkp_dev_download(ctx, total.v, wk.acc() + n, 32));
     grand_product_ok = (total == one);
     auto t = std::chrono::steady_clock::now();
+    if (tm.precise) { zkp_ctx_synchronize(ctx); t = std::chrono::steady_clock::now(); }
     PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.acc(), log_n, 1, 1, nullptr));  // prover.rs:374: acc evaluations -> coefficients
+    if (tm.precise) zkp_ctx_synchronize(ctx);
     tm.ntt += Timers::since(t);
     PLONK_TRY(zkp_dev_copy(ctx, wk.coef(3), wk.acc(), n * 32));
     const size_t idx[6] = {0, 1, 2, n, n + 1, n + 2};  // + (b7 X^2 + b8 X + b9)(X^n - 1)
@@ -714,8 +719,10 @@ static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uin
   {
     PLONK_TRY(zkp_dev_zero(ctx, wk.cos(0), 4 * d * 32));
     for (int k = 0; k < 4; k++) PLONK_TRY(zkp_dev_copy(ctx, wk.cos(k), wk.coef(k), (n + 3) * 32));
+    if (tm.precise) zkp_ctx_synchronize(ctx);
     auto t = std::chrono::steady_clock::now();
     PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.cos(0), cc->log_d, 4, 0, cc->coset_h.v));
+    if (tm.precise) zkp_ctx_synchronize(ctx);
     tm.ntt += Timers::since(t);
     zkp_plonk_quotient_args q;
     memset(&q, 0, sizeof(q));
@@ -738,8 +745,10 @@ static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uin
     q.rho = cc->rho;
     q.t_dev = wk.t();
     PLONK_TRY(zkp_plonk_quotient_dev(ctx, &q));
+    if (tm.precise) zkp_ctx_synchronize(ctx);
     t = std::chrono::steady_clock::now();
     PLONK_TRY(zkp_ntt_fr_dev(ctx, wk.t(), cc->log_d, 1, 1, cc->coset_h.v));
+    if (tm.precise) zkp_ctx_synchronize(ctx);
     tm.ntt += Timers::since(t);
   }
   // SlicePoly::new (slice_polynomial.rs:22-43) on the trimmed quotient

@@ -245,7 +245,7 @@ def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int], p
     ev = fields.fr_from_mont_array(np.frombuffer(bytes(ps.evaluations), dtype=np.uint64).reshape(6, 4))
     u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
     return Proof(*cm, *ev, u, int(ps.degree),
-                 timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "host": tm[3]})
+                 timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "other": tm[3]})
 
 
 def chain_circuit(n_gates: int, seed: int) -> Circuit:
@@ -316,4 +316,4 @@ def generate_proof_sharded(compiled_circuit: CompiledCircuit, blinding: Sequence
     cm = fields.g1_from_array(np.frombuffer(bytes(ps.commitments), dtype=np.uint64).reshape(9, 12))
     ev = fields.fr_from_mont_array(np.frombuffer(bytes(ps.evaluations), dtype=np.uint64).reshape(6, 4))
     u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
-    return Proof(*cm, *ev, u, int(ps.degree), timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "host": tm[3]})
+    return Proof(*cm, *ev, u, int(ps.degree), timings_ms={"total": tm[0], "msm": tm[1], "ntt": tm[2], "other": tm[3]})
