@@ -325,7 +325,17 @@ def l1_poly(n):
     return interpolate([1] + [0] * (n - 1), n)
 
 
-def generate_proof(cc: CompiledCircuit, srs, blinding: Sequence[int]) -> Proof:
+def generate_proof(cc: CompiledCircuit, srs, blinding: Sequence[int], commit_fn=None) -> Proof:
+    """`commit_fn(coeffs) -> point` replaces the pure-Python MSM (the C oracle's evaluate_in_s restatement is used by
+    the larger test circuits; the reference's own circuits keep the all-Python path)."""
+    global commit
+    if commit_fn is not None:
+        py_commit = commit
+        commit = lambda poly, _srs: commit_fn(poly)  # noqa: E731
+        try:
+            return generate_proof(cc, srs, blinding)
+        finally:
+            commit = py_commit
     b1, b2, b3, b4, b5, b6, b7, b8, b9 = [x % R for x in blinding]
     n = cc.size
     w = o.root_of_unity(n)

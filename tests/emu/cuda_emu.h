@@ -151,7 +151,44 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
 }
 }  // namespace zkp_emu
 
+namespace zkp_emu {
+// Kernels that never synchronise (no __syncthreads, no shuffles, no __shared__): the CUDA threads of a block run
+// one after another on one OS thread and the blocks are spread over the host cores -- no barrier traffic at all.
+// Calling a barrier from such a kernel dereferences the null state and crashes, which is the check.
+template <class Body>
+void launch_nosync(dim3 grid, dim3 block, Body body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+  unsigned workers = std::thread::hardware_concurrency();
+  if (workers == 0) workers = 4;
+  if (workers > 16) workers = 16;
+  if ((size_t)workers > nblocks) workers = (unsigned)nblocks;
+  auto run = [&](unsigned wi) {
+    blockDim = block;
+    gridDim = grid;
+    for (size_t b = wi; b < nblocks; b += workers) {
+      blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((size_t)grid.x * grid.y)));
+      for (unsigned tid = 0; tid < nthreads; tid++) {
+        zkp_emu_tid = tid;
+        threadIdx = dim3(tid % block.x, (tid / block.x) % block.y, tid / (block.x * block.y));
+        body();
+      }
+    }
+  };
+  if (workers <= 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> th;
+    th.reserve(workers);
+    for (unsigned w = 0; w < workers; w++) th.emplace_back(run, w);
+    for (auto& t : th) t.join();
+  }
+}
+}  // namespace zkp_emu
+
 // Kernel launch + dynamic shared memory vocabulary shared with the real build (see csrc/runtime.h).
 #define ZKP_LAUNCH(kernel, grid, block, smem, stream, ...) \
   zkp_emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define ZKP_LAUNCH_NOSYNC(kernel, grid, block, smem, stream, ...) \
+  zkp_emu::launch_nosync((grid), (block), [&]() { kernel(__VA_ARGS__); })
 #define ZKP_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(zkp_emu::dyn_smem())

@@ -37,7 +37,7 @@ def _ref_proof_bytes(p):
     return out + int(p.degree).to_bytes(8, "little")
 
 
-def _prove_both(zkp, engine, pyref, rc, blinding=BLIND):
+def _prove_both(zkp, engine, pyref, rc, blinding=BLIND, coracle=None):
     cc_ref = rc.compile()
     srs_pts = pyref.srs_from_secret(SECRET, cc_ref.size)
     srs = zkp.Srs.new_from_secret(engine, SECRET, cc_ref.size)
@@ -53,7 +53,18 @@ def _prove_both(zkp, engine, pyref, rc, blinding=BLIND):
     proof = zkp.plonk.generate_proof(cc, blinding)
     # the two native provers (coset-evaluation quotient vs one GPU product per `&a * &b`) agree byte for byte
     assert zkp.plonk.generate_proof(cc, blinding, products=True).to_bytes() == proof.to_bytes()
-    want = ref.generate_proof(cc_ref, srs_pts, blinding)
+    commit_fn = None
+    if coracle is not None:  # larger circuits: the C oracle's literal evaluate_in_s restatement does the G1 sums
+        F = zkp.fields
+        limbs = srs.g1_limbs()
+
+        def commit_fn(poly):
+            if not len(limbs) > max(len(poly) - 1, 0):
+                raise AssertionError("g1_points.len() > polynomial.degree()")
+            if not poly:
+                return None
+            return F.g1_from_array(coracle.msm_naive(F.fr_to_mont_array(poly), limbs[:len(poly)]))[0]
+    want = ref.generate_proof(cc_ref, srs_pts, blinding, commit_fn=commit_fn)
     return proof, want, cc_ref, srs_pts
 
 
@@ -104,9 +115,9 @@ def _chain_circuit(n_gates, seed):
 
 
 @pytest.mark.parametrize("n_gates", [13, 32, 61])
-def test_chain_circuit_byte_identical(zkp, engine, pyref, n_gates):
+def test_chain_circuit_byte_identical(zkp, engine, pyref, coracle, n_gates):
     rc = _chain_circuit(n_gates, seed=n_gates)
-    proof, want, cc_ref, srs_pts = _prove_both(zkp, engine, pyref, rc)
+    proof, want, cc_ref, srs_pts = _prove_both(zkp, engine, pyref, rc, coracle=coracle)
     assert proof.to_bytes() == _ref_proof_bytes(want)
     assert ref.verify_with_secret(cc_ref, srs_pts, SECRET, want)
     assert proof.degree == want.degree == cc_ref.size + 1  # t has 3n + 6 coefficients -> slices of n + 2

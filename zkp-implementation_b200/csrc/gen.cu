@@ -90,7 +90,7 @@ int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out);
 static int normalise(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) { return normalise_dev(ctx, tmp, n, out); }
 int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) {
   const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
-  ZKP_LAUNCH(batch_normalise_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+  ZKP_LAUNCH_NOSYNC(batch_normalise_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
              ctx->stream, tmp, n, out);
   return rt::check_last();
 }
@@ -120,7 +120,7 @@ int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
   ZKP_TRY(rt::h2d(step_d, &step, sizeof(step), ctx->stream));
   ZKP_TRY(rt::sync(ctx->stream));
   const size_t threads = (n + CHAIN_LEN - 1) / CHAIN_LEN;
-  ZKP_LAUNCH(gen_chain_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+  ZKP_LAUNCH_NOSYNC(gen_chain_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
              ctx->stream, start_d, step_d, n, tmp.as<G1Xyzz>());
   int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
   if (st == ZKP_OK) st = rt::sync(ctx->stream);
@@ -133,7 +133,7 @@ int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t start, size_t n, G1Affine* ou
   DevBuf tmp;
   ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
   const size_t threads = (n + SRS_RUN - 1) / SRS_RUN;
-  ZKP_LAUNCH(gen_srs_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
+  ZKP_LAUNCH_NOSYNC(gen_srs_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
              ctx->stream, secret, start, n, tmp.as<G1Xyzz>());
   int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
   if (st == ZKP_OK) st = rt::sync(ctx->stream);

@@ -38,7 +38,11 @@
 namespace zkp {
 
 static constexpr uint32_t ACC_THREADS = 128;
+#ifdef ZKP_EMU
+static constexpr uint32_t RED_THREADS = 32;   // emulated build: one OS thread per CUDA thread, keep the blocks small
+#else
 static constexpr uint32_t RED_THREADS = 128;
+#endif
 static constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmTask {
@@ -127,11 +131,11 @@ __global__ void __launch_bounds__(256) msm_task_count_kernel(const uint32_t* __r
 }
 
 // One block per heavy bucket: partials[off] = sum of its nt partials (the reduction then reads one entry).
-__global__ void __launch_bounds__(128) msm_heavy_fold_kernel(const uint32_t* __restrict__ heavy,
+__global__ void __launch_bounds__(RED_THREADS) msm_heavy_fold_kernel(const uint32_t* __restrict__ heavy,
                                                              const uint32_t* __restrict__ task_off,
                                                              const uint32_t* __restrict__ ntask,
                                                              G1Xyzz* __restrict__ partials, uint32_t* __restrict__ nfold) {
-  __shared__ G1Xyzz sh[128];
+  __shared__ G1Xyzz sh[RED_THREADS];
   const uint32_t tid = threadIdx.x;
   uint32_t count = heavy[0];
   if (count > HEAVY_CAP) count = HEAVY_CAP;
@@ -547,7 +551,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     for (uint32_t j = 0; j < count; j++) {
       const uint32_t n = (uint32_t)n_list[j];
       if (!n) continue;
-      ZKP_LAUNCH(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars_list[j], n, c, nwin,
+      ZKP_LAUNCH_NOSYNC(msm_recode_kernel, dim3((n + 255) / 256), dim3(256), 0, st, scalars_list[j], n, c, nwin,
                  (uint32_t)table_stride, fixed ? 1u : 0u, j, total_buckets, keys_a + off, vals_a + off);
       ctx->msm_launches++;
       off += (size_t)n * nwin;
@@ -565,16 +569,16 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    ZKP_LAUNCH(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, keys_b, total, total_buckets, bstart, bend);
+    ZKP_LAUNCH_NOSYNC(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, keys_b, total, total_buckets, bstart, bend);
     ctx->msm_launches++;
   }
   // 4. tasks
   ZKP_TRY(rt::dev_memset(ntask + total_buckets, 0, 4, st));
   ZKP_TRY(rt::dev_memset(heavy, 0, 4, st));
-  ZKP_LAUNCH(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, total_buckets, smax,
+  ZKP_LAUNCH_NOSYNC(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, total_buckets, smax,
              ntask, heavy);
   ZKP_TRY(exclusive_scan_u32(ctx, ntask, task_off, total_buckets + 1));
-  ZKP_LAUNCH(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
+  ZKP_LAUNCH_NOSYNC(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
              total_buckets, smax, tasks, task_len, task_id);
   ctx->msm_launches += 3;
   uint32_t ntasks = 0;
@@ -586,16 +590,16 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     uint32_t len_bits = 1;
     while ((1u << len_bits) <= smax) len_bits++;
     ZKP_TRY(sort_tasks_desc(ctx, task_len, task_len_sorted, task_id, task_order, ntasks, len_bits));
-    ZKP_LAUNCH(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
+    ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
                task_order, ntasks, vals_b, bases, partials);
     ctx->msm_launches += 3;
   }
   // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
   phase_mark(ctx, 4);
   ZKP_TRY(rt::d2d(nfold, ntask, (size_t)total_buckets * 4, st));
-  ZKP_LAUNCH(msm_heavy_fold_kernel, dim3(ctx->sm_count * 4), dim3(128), 0, st, (const uint32_t*)heavy,
+  ZKP_LAUNCH(msm_heavy_fold_kernel, dim3(ctx->sm_count * 4), dim3(RED_THREADS), 0, st, (const uint32_t*)heavy,
              (const uint32_t*)task_off, (const uint32_t*)ntask, partials, nfold);
-  ZKP_LAUNCH(msm_bucket_gather_kernel, dim3((total_buckets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
+  ZKP_LAUNCH_NOSYNC(msm_bucket_gather_kernel, dim3((total_buckets + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
              (const G1Xyzz*)partials, (const uint32_t*)task_off, (const uint32_t*)nfold, total_buckets, lvl_buf);
   ctx->msm_launches += 2;
   {
@@ -608,7 +612,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
       lv.off[l] = (uint32_t)off;
       lv.m[l] = mm;
       const uint32_t pairs = (mm >> 1) * nsets;
-      ZKP_LAUNCH(msm_pair_add_kernel, dim3((pairs + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
+      ZKP_LAUNCH_NOSYNC(msm_pair_add_kernel, dim3((pairs + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
                  (const G1Xyzz*)(lvl_buf + off), pairs, lvl_buf + off + (size_t)mm * nsets);
       ctx->msm_launches++;
       off += (size_t)mm * nsets;
@@ -662,7 +666,7 @@ int msm_precompute_dev(Ctx* ctx, uint32_t c) {
   int st = tmp.reserve(n * sizeof(G1Xyzz));
   if (st == ZKP_OK) st = rt::d2d(ctx->srs_tab, ctx->srs, n * sizeof(G1Affine), ctx->stream);
   for (uint32_t w = 1; w < nwin && st == ZKP_OK; w++) {
-    ZKP_LAUNCH(msm_shift_window_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, ctx->stream,
+    ZKP_LAUNCH_NOSYNC(msm_shift_window_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, ctx->stream,
                (const G1Affine*)(ctx->srs_tab + (size_t)(w - 1) * n), n, c, tmp.as<G1Xyzz>());
     st = normalise_dev(ctx, tmp.as<G1Xyzz>(), n, ctx->srs_tab + (size_t)w * n);
   }

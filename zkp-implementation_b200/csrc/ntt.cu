@@ -595,7 +595,7 @@ int ntt_dist_permute_dev(Ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, uint32
   size_t blocks = (total + 255) / 256;
   const size_t cap = (size_t)ctx->sm_count * 16;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(ntt_dist_permute_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, in, out, rows_log, world_log,
+  ZKP_LAUNCH_NOSYNC(ntt_dist_permute_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, in, out, rows_log, world_log,
              cols_log, inverse ? 1u : 0u);
   return rt::check_last();
 }
@@ -605,7 +605,7 @@ int fr_pointwise_mul_dev(Ctx* ctx, Fr* a, const Fr* b, size_t n) {
   size_t blocks = (n + 255) / 256;
   const size_t cap = (size_t)ctx->sm_count * 16;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(fr_pointwise_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, a, b, n);
+  ZKP_LAUNCH_NOSYNC(fr_pointwise_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, a, b, n);
   return rt::check_last();
 }
 

@@ -21,7 +21,11 @@
 
 namespace zkp {
 
+#ifdef ZKP_EMU
+static constexpr uint32_t PT = 64;   // emulated build: one OS thread per CUDA thread, keep the blocks small
+#else
 static constexpr uint32_t PT = 256;
+#endif
 static constexpr uint32_t POW_CHUNK = 64;
 static constexpr uint32_t INV_CHUNK = 16;
 static constexpr uint32_t SCAN_PER_THREAD = 8;
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(PT) fr_powers_kernel(Fr* out, Fr base, Fr firs
 
 int fr_powers_dev(Ctx* ctx, Fr* out, const Fr& base, const Fr& first, size_t n) {
   if (!n) return ZKP_OK;
-  ZKP_LAUNCH(fr_powers_kernel, dim3(blocks_for(n, PT * POW_CHUNK)), dim3(PT), 0, ctx->stream, out, base, first, n);
+  ZKP_LAUNCH_NOSYNC(fr_powers_kernel, dim3(blocks_for(n, PT * POW_CHUNK)), dim3(PT), 0, ctx->stream, out, base, first, n);
   return rt::check_last();
 }
 
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(PT) fr_batch_inverse_kernel(Fr* data, size_t n
 
 int fr_batch_inverse_dev(Ctx* ctx, Fr* data, size_t n) {
   if (!n) return ZKP_OK;
-  ZKP_LAUNCH(fr_batch_inverse_kernel, dim3(blocks_for(n, PT * INV_CHUNK)), dim3(PT), 0, ctx->stream, data, n);
+  ZKP_LAUNCH_NOSYNC(fr_batch_inverse_kernel, dim3(blocks_for(n, PT * INV_CHUNK)), dim3(PT), 0, ctx->stream, data, n);
   return rt::check_last();
 }
 
@@ -149,7 +153,7 @@ static int fr_scan_rec(Ctx* ctx, Fr* data, size_t n, bool reverse, Fr* scratch) 
              reverse ? 1u : 0u);
   if (nb > 1) {
     ZKP_TRY(fr_scan_rec<OP>(ctx, scratch, nb, false, scratch + nb));
-    ZKP_LAUNCH(fr_scan_apply_kernel<OP>, dim3(nb - 1), dim3(PT), 0, ctx->stream, data, n, scratch, reverse ? 1u : 0u);
+    ZKP_LAUNCH_NOSYNC(fr_scan_apply_kernel<OP>, dim3(nb - 1), dim3(PT), 0, ctx->stream, data, n, scratch, reverse ? 1u : 0u);
   }
   return rt::check_last();
 }
@@ -180,7 +184,7 @@ int fr_lincomb_dev(Ctx* ctx, Fr* out, size_t out_len, const LincombArgs& a) {
   unsigned blocks = blocks_for(out_len, PT);
   const unsigned cap = (unsigned)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(fr_lincomb_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, out, out_len, a);
+  ZKP_LAUNCH_NOSYNC(fr_lincomb_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, out, out_len, a);
   return rt::check_last();
 }
 
@@ -193,7 +197,7 @@ __global__ void fr_add_at_kernel(Fr* data, SparseAddArgs a) {
 int fr_add_at_dev(Ctx* ctx, Fr* data, const SparseAddArgs& a) {
   if (!a.count) return ZKP_OK;
   if (a.count > SparseAddArgs::MAX_TERMS) return ZKP_ERR_INVALID_ARG;
-  ZKP_LAUNCH(fr_add_at_kernel, dim3(1), dim3(32), 0, ctx->stream, data, a);
+  ZKP_LAUNCH_NOSYNC(fr_add_at_kernel, dim3(1), dim3(32), 0, ctx->stream, data, a);
   return rt::check_last();
 }
 
@@ -278,7 +282,7 @@ int fr_trimmed_len_dev(Ctx* ctx, const Fr* coeffs, size_t n, size_t* out_len) {
   unsigned blocks = blocks_for(n, PT);
   const unsigned cap = (unsigned)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(fr_trimmed_len_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, coeffs, n, d);
+  ZKP_LAUNCH_NOSYNC(fr_trimmed_len_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, coeffs, n, d);
   unsigned h = 0;
   ZKP_TRY(rt::d2h(&h, d, sizeof(unsigned), ctx->stream));
   ZKP_TRY(rt::sync(ctx->stream));
@@ -312,7 +316,7 @@ int plonk_numden_dev(Ctx* ctx, const PlonkNumDenArgs& p) {
   unsigned blocks = blocks_for(p.n, PT);
   const unsigned cap = (unsigned)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(plonk_numden_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, p);
+  ZKP_LAUNCH_NOSYNC(plonk_numden_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, p);
   return rt::check_last();
 }
 
@@ -359,7 +363,7 @@ int plonk_quotient_dev(Ctx* ctx, const PlonkQuotientArgs& p) {
   unsigned blocks = blocks_for(p.d, PT);
   const unsigned cap = (unsigned)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(plonk_quotient_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, p);
+  ZKP_LAUNCH_NOSYNC(plonk_quotient_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, p);
   return rt::check_last();
 }
 
@@ -391,7 +395,7 @@ int plonk_gate_check_dev(Ctx* ctx, const Fr* const cols[9], size_t n, bool* ok) 
   unsigned blocks = blocks_for(n, PT);
   const unsigned cap = (unsigned)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ZKP_LAUNCH(plonk_gate_check_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, cols[0], cols[1], cols[2], cols[3], cols[4],
+  ZKP_LAUNCH_NOSYNC(plonk_gate_check_kernel, dim3(blocks), dim3(PT), 0, ctx->stream, cols[0], cols[1], cols[2], cols[3], cols[4],
              cols[5], cols[6], cols[7], cols[8], n, d);
   unsigned h = 0;
   ZKP_TRY(rt::d2h(&h, d, sizeof(unsigned), ctx->stream));
@@ -415,7 +419,7 @@ int g1_scalar_mul_dev(Ctx* ctx, const G1Affine* base_dev, const Fr* scalars_host
   Fr* ds = ctx->eval_partials.as<Fr>();
   G1Xyzz* dout = reinterpret_cast<G1Xyzz*>(ds + 64);
   ZKP_TRY(rt::h2d(ds, scalars_host, count * sizeof(Fr), ctx->stream));
-  ZKP_LAUNCH(g1_scalar_mul_kernel, dim3(count), dim3(1), 0, ctx->stream, base_dev, (const Fr*)ds, count, dout);
+  ZKP_LAUNCH_NOSYNC(g1_scalar_mul_kernel, dim3(count), dim3(1), 0, ctx->stream, base_dev, (const Fr*)ds, count, dout);
   ZKP_TRY(rt::d2h(out_host, dout, count * sizeof(G1Xyzz), ctx->stream));
   ZKP_TRY(rt::sync(ctx->stream));
   return rt::check_last();

@@ -48,6 +48,9 @@ inline const char* last_error_string() { return "emulator"; }
 #include <cuda_runtime.h>
 #include <string.h>
 #define ZKP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// kernels without barriers / shuffles / shared memory: same launch here; the CPU emulator runs them without its
+// per-thread barrier machinery (tests/emu/cuda_emu.h)
+#define ZKP_LAUNCH_NOSYNC(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZKP_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char zkp_dyn_smem_raw[]; \
   type* name = reinterpret_cast<type*>(zkp_dyn_smem_raw)

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -196,6 +197,7 @@ struct zkp_plonk_compiled {
   Fr* d_cos = nullptr;          // 11 x d: coset evaluations of q_l q_r q_o q_m q_c pi s1 s2 s3 L1, then the points x_i
   Fr* d_work = nullptr;         // prover workspace (see Work below)
   size_t work_elems = 0;
+  std::mutex prove_mu;          // one proof at a time per compiled circuit: the workspace is shared
   ~zkp_plonk_compiled() {
     if (ctx) {
       zkp_dev_free(ctx, d_vals);
@@ -639,6 +641,7 @@ static int prove_device(zkp_ctx* ctx, const zkp_plonk_compiled* cc_in, const uin
                         double* timings_ms, const Shard& sh) {
   if (!ctx || !cc_in || !blinding || !out || cc_in->ctx != ctx) return ZKP_B200_ERR_INVALID_ARG;
   zkp_plonk_compiled* cc = const_cast<zkp_plonk_compiled*>(cc_in);  // the workspace is a cache, not circuit state
+  std::lock_guard<std::mutex> prove_lock(cc->prove_mu);
   DevTimers tm;
   tm.precise = timings_ms != nullptr;
   const size_t n = cc->size, d = cc->d;
