@@ -78,7 +78,11 @@ struct FrParams {
   // r = ...ffffffff00000001: limb 0 is 1, limb 1 is 2^32 - 1 and -r^-1 = -1 (mod 2^32), so in every
   // Montgomery reduction step m = -t0, m * r[0] is an addition and m * r[1] = (m << 32) - m is two ALU
   // ops: 6 instead of 8 multiply-adds per step (112 instead of 128 per product).
+#ifdef ZKP_FR_GENERIC_REDC
+  static constexpr bool LOW_LIMBS_SPECIAL = false;  // experiment knob: plain CIOS reduction rows
+#else
   static constexpr bool LOW_LIMBS_SPECIAL = true;
+#endif
   static constexpr uint32_t M0 = 0xffffffffu;  // -r^-1 mod 2^32
   ZKP_HD static constexpr uint32_t mod(int i) {
     constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,

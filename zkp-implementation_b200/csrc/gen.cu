@@ -1,8 +1,10 @@
 // Setup-time generators and the integer-pipe microbenchmark.
 //
 //  * gen_srs_dev      `Srs::new_from_secret` (kzg/src/srs.rs:48-69): [secret^i * G]_{i<n}, affine.
-//                     The reference runs n serial scalar multiplications with one Fq inversion
-//                     each; here every thread owns a short run of consecutive powers and the
+//                     The reference runs n serial scalar multiplications (255 doublings + ~128
+//                     additions and one Fq inversion each).  Here the generator is a FIXED base: a
+//                     32 x 256 table of d * 2^(8w) * G turns every scalar multiplication into 32 mixed
+//                     additions, every thread owns a short run of consecutive powers, and the
 //                     normalisation uses Montgomery's batch-inversion trick.
 //  * gen_bases_dev    n distinct pseudo-random points (a0 + i*delta)*G for benchmark configs 2/5
 //                     ("random points, not an SRS with known structure" -- SURVEY.md 8d).
@@ -34,17 +36,38 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_chain_kernel(const G1Xyzz* st
   }
 }
 
-// tmp[i] = secret^i * G (XYZZ): MSB-first double-and-add over the canonical power, as ark-ec does
+// Fixed-base table of the generator: gtab[w * 256 + d] = d * 2^(8w) * G (d = 0 is the point at infinity).
+// Row w is built by one thread walking d = 1 .. 255 with mixed additions of 2^(8w) G.
+static constexpr uint32_t GTAB_WINDOWS = 32, GTAB_DIGITS = 256;
+
+__global__ void gen_gtab_kernel(G1Xyzz* tab) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= GTAB_WINDOWS) return;
+  G1Xyzz base = G1Xyzz::from_affine(g1_generator());
+  for (uint32_t k = 0; k < 8 * w; k++) base = xyzz_dbl(base);
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (uint32_t d = 0; d < GTAB_DIGITS; d++) {
+    st_xyzz(tab + (size_t)w * GTAB_DIGITS + d, acc);
+    xyzz_add(acc, base);
+  }
+}
+
+// tmp[i] = secret^(start + i) * G (XYZZ) = sum over the 32 bytes of the canonical power of a table entry
 // (`start`: index of the first power, for a rank that owns a point range of a sharded SRS)
-__global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t start, size_t n, G1Xyzz* tmp) {
+__global__ void __launch_bounds__(GEN_THREADS) gen_srs_kernel(Fr secret, size_t start, size_t n,
+                                                              const G1Affine* __restrict__ gtab, G1Xyzz* tmp) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t first = t * SRS_RUN;
   if (first >= n) return;
   Fr cur = fp_pow_u64(secret, (uint64_t)(start + first));
-  const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
   for (uint32_t i = 0; i < SRS_RUN && first + i < n; i++) {
-    Fr k = fp_from_mont(cur);
-    st_xyzz(tmp + first + i, xyzz_mul_limbs(g, k.v, 8));
+    const Fr k = fp_from_mont(cur);
+    G1Xyzz acc = G1Xyzz::infinity();
+    for (uint32_t w = 0; w < GTAB_WINDOWS; w++) {
+      const uint32_t d = (k.v[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+      if (d) xyzz_madd(acc, ld_affine(gtab + (size_t)w * GTAB_DIGITS + d));
+    }
+    st_xyzz(tmp + first + i, acc);
     cur = fp_mul(cur, secret);
   }
 }
@@ -130,14 +153,23 @@ int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
 
 int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t start, size_t n, G1Affine* out) {
   if (n == 0) return ZKP_OK;
-  DevBuf tmp;
-  ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz)));
+  const size_t tab_n = (size_t)GTAB_WINDOWS * GTAB_DIGITS;
+  DevBuf tmp, tab;
+  const size_t tmp_n = n > tab_n ? n : tab_n;
+  ZKP_TRY(tmp.reserve(tmp_n * sizeof(G1Xyzz)));
+  int st0 = tab.reserve(tab_n * sizeof(G1Affine));
+  if (st0 != ZKP_OK) { tmp.release(); return st0; }
+  // the generator's window table (XYZZ in tmp, normalised into tab)
+  ZKP_LAUNCH_NOSYNC(gen_gtab_kernel, dim3(1), dim3(GTAB_WINDOWS), 0, ctx->stream, tmp.as<G1Xyzz>());
+  st0 = normalise(ctx, tmp.as<G1Xyzz>(), tab_n, tab.as<G1Affine>());
+  if (st0 != ZKP_OK) { tmp.release(); tab.release(); return st0; }
   const size_t threads = (n + SRS_RUN - 1) / SRS_RUN;
   ZKP_LAUNCH_NOSYNC(gen_srs_kernel, dim3((unsigned)((threads + GEN_THREADS - 1) / GEN_THREADS)), dim3(GEN_THREADS), 0,
-             ctx->stream, secret, start, n, tmp.as<G1Xyzz>());
+             ctx->stream, secret, start, n, (const G1Affine*)tab.as<G1Affine>(), tmp.as<G1Xyzz>());
   int st = normalise(ctx, tmp.as<G1Xyzz>(), n, out);
   if (st == ZKP_OK) st = rt::sync(ctx->stream);
   tmp.release();
+  tab.release();
   return st;
 }
 
