@@ -177,6 +177,11 @@ int zkp_fr_trimmed_len_dev(zkp_ctx* ctx, const void* coeffs_dev, size_t n, size_
 /* `KzgScheme::commit_para` (kzg/src/scheme.rs:78-82) for `count` <= 64 scalars at once: scalars[k] * srs[0] */
 int zkp_g1_mul_srs0(zkp_ctx* ctx, const uint64_t* scalars, uint32_t count, uint64_t* out_xy /* count x 12 */);
 
+/* ---- the MSM's grouping step on its own: stable LSD radix sort of n (key, value) u32 pairs by the low key_bits of
+ *      the key (descending != 0: largest first), in place on device arrays; and the exclusive u32 scan it uses. ---- */
+int zkp_sort_pairs_dev(zkp_ctx* ctx, void* keys_dev, void* vals_dev, size_t n, uint32_t key_bits, int descending);
+int zkp_scan_exclusive_u32_dev(zkp_ctx* ctx, const void* in_dev, void* out_dev, size_t n);
+
 /* ---- synthetic workloads (bench configs 2/5): n distinct pseudo-random G1 points generated on
  *      the device from a seed (a0 + i*delta) * G, affine, written to bases_dev (n x 96 B). ----- */
 int zkp_g1_generate_bases_dev(zkp_ctx* ctx, uint64_t seed, size_t n, void* bases_dev);

@@ -84,8 +84,16 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   return zkp_emu_shfl(v, lane + d < 32 ? lane + d : lane);
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
+  // one exchange round: every lane publishes its predicate, then reads the whole warp's
+  auto* st = zkp_emu::state();
+  const unsigned w = zkp_emu_tid >> 5, lane = zkp_emu_tid & 31;
+  st->warp_slots[w * 32 + lane] = pred ? 1u : 0u;
+  pthread_barrier_wait(&st->warp_barriers[w]);
+  const unsigned base = w * 32;
+  const unsigned nl = std::min(32u, st->nthreads - base);
   unsigned acc = 0;
-  for (unsigned l = 0; l < 32; l++) acc |= (zkp_emu_shfl<unsigned>(pred ? 1u : 0u, l) & 1u) << l;
+  for (unsigned l = 0; l < nl; l++) acc |= (unsigned)(st->warp_slots[base + l] & 1u) << l;
+  pthread_barrier_wait(&st->warp_barriers[w]);
   return acc;
 }
 

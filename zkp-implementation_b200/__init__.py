@@ -88,6 +88,9 @@ ABI = {
     "zkp_fr_trimmed_len_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                               ctypes.POINTER(ctypes.c_size_t)]),
     "zkp_g1_mul_srs0": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
+    "zkp_sort_pairs_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                          ctypes.c_int]),
+    "zkp_scan_exclusive_u32_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zkp_g1_generate_bases_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p]),
     "zkp_bench_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
@@ -382,6 +385,13 @@ class Engine:
         out = np.zeros((len(scalars), 12), dtype=np.uint64)
         self._check(self.lib.zkp_g1_mul_srs0(self._h, _ptr(sa), len(scalars), _ptr(out)))
         return fields.g1_from_array(out)
+
+    # -- radix sort / scan (csrc/sort.cu) -----------------------------------------------------------
+    def sort_pairs_dev(self, keys_dev, vals_dev, n: int, key_bits: int, descending: bool = False) -> None:
+        self._check(self.lib.zkp_sort_pairs_dev(self._h, _ptr(keys_dev), _ptr(vals_dev), n, key_bits, 1 if descending else 0))
+
+    def scan_exclusive_u32_dev(self, in_dev, out_dev, n: int) -> None:
+        self._check(self.lib.zkp_scan_exclusive_u32_dev(self._h, _ptr(in_dev), _ptr(out_dev), n))
 
     # -- synthetic workloads / microbenchmarks ----------------------------------------------------
     def generate_bases_dev(self, seed: int, n: int, bases_dev) -> None:

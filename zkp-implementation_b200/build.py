@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu", "poly.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu", "poly.cu", "sort.cu"]
 HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
 HOST_DIR = os.path.join(PKG, "host")
 HOST_SOURCES = ["plonk.cpp", "kzg.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++

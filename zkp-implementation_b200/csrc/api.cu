@@ -633,6 +633,30 @@ int zkp_plonk_gate_check_dev(zkp_ctx* h, const void* const cols_dev[9], size_t n
   return ZKP_OK;
 }
 
+// ---- radix sort / scan --------------------------------------------------------------------------------
+int zkp_sort_pairs_dev(zkp_ctx* h, void* keys_dev, void* vals_dev, size_t n, uint32_t key_bits, int descending) {
+  ZKP_ENTER(h);
+  if (n >= ((size_t)1 << 31) || key_bits > 32 || (n && (!keys_dev || !vals_dev))) return ZKP_ERR_INVALID_ARG;
+  if (!n) return ZKP_OK;
+  ZKP_TRY(c->msm.sort_tmp.reserve(2 * n * sizeof(uint32_t)));
+  uint32_t* k1 = c->msm.sort_tmp.as<uint32_t>();
+  uint32_t* v1 = k1 + n;
+  uint32_t *kres = nullptr, *vres = nullptr;
+  ZKP_TRY(radix_sort_pairs_dev(c, (uint32_t*)keys_dev, (uint32_t*)vals_dev, k1, v1, (uint32_t)n, key_bits, descending != 0,
+                               &kres, &vres));
+  if (kres != keys_dev) {
+    ZKP_TRY(rt::d2d(keys_dev, kres, n * sizeof(uint32_t), c->stream));
+    ZKP_TRY(rt::d2d(vals_dev, vres, n * sizeof(uint32_t), c->stream));
+  }
+  return rt::check_last();
+}
+
+int zkp_scan_exclusive_u32_dev(zkp_ctx* h, const void* in_dev, void* out_dev, size_t n) {
+  ZKP_ENTER(h);
+  if (n >= ((size_t)1 << 32) || (n && (!in_dev || !out_dev))) return ZKP_ERR_INVALID_ARG;
+  return scan_exclusive_u32_dev(c, (const uint32_t*)in_dev, (uint32_t*)out_dev, (uint32_t)n);
+}
+
 // ---- synthetic workloads / microbenchmarks ------------------------------------------------------
 int zkp_g1_generate_bases_dev(zkp_ctx* h, uint64_t seed, size_t n, void* bases_dev) {
   if (!h || (n && !bases_dev)) return ZKP_ERR_INVALID_ARG;

@@ -81,6 +81,7 @@ struct Ctx {
   static constexpr uint32_t EVAL_SLOTS = 16;
   static constexpr uint32_t EVAL_PARTIALS = 4096;  // blocks of 256 x 32 coefficients: up to 2^25 coefficients
   DevBuf poly_scratch, eval_out, eval_partials;
+  DevBuf sort_scan, sort_hist;  // sort.cu: tile sums of the u32 scan; digit histograms / offsets [digit][tile]
 
   // MSM state
   MsmScratch msm;
@@ -118,6 +119,13 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size
 int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_list, uint32_t count, const G1Affine* bases,
                       G1Xyzz* out_host, uint32_t fixed_c, size_t table_stride);
 int msm_precompute_dev(Ctx* ctx, uint32_t window_bits);
+
+// ---- sort / scan (sort.cu) ----
+// Stable LSD radix sort of n (key, value) pairs by the low key_bits of the key; the result is in (*kres, *vres), one
+// of the two buffer pairs (both are clobbered).
+int radix_sort_pairs_dev(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, uint32_t key_bits,
+                         bool descending, uint32_t** kres, uint32_t** vres);
+int scan_exclusive_u32_dev(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n);
 void msm_destroy(Ctx* ctx);
 
 }  // namespace zkp

@@ -9,7 +9,7 @@
 // Pipeline (all on one stream):
 //   1. recode      scalars: Montgomery -> canonical -> W signed c-bit digits; one (bucket, point|sign)
 //                  pair per digit
-//   2. sort        ONE radix sort of all n*W pairs by global bucket id (cub::DeviceRadixSort)
+//   2. sort        ONE radix sort of all n*W pairs by global bucket id (sort.cu: stable LSD, 8-bit digits)
 //   3. boundaries  start/end of every bucket's run in the sorted order
 //   4. tasks       buckets longer than S_max are split so no thread owns an unbounded run; the task
 //                  list is sorted by run length (longest first) so the 32 lanes of a warp finish together
@@ -28,9 +28,10 @@
 #include "engine.h"
 #include "memops.cuh"
 
-#ifndef ZKP_EMU
+#if defined(ZKP_USE_CUB) && !defined(ZKP_EMU)
 #include <cub/cub.cuh>
-#else
+#endif
+#ifdef ZKP_EMU
 #include <algorithm>
 #include <numeric>
 #endif
@@ -375,56 +376,24 @@ static uint32_t choose_window_bits(size_t n, bool fixed) {
   return best;
 }
 
-static int sort_window(Ctx* ctx, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n,
-                       uint32_t key_bits) {
-#ifdef ZKP_EMU
-  (void)ctx; (void)key_bits;
-  std::vector<uint32_t> idx(n);
-  std::iota(idx.begin(), idx.end(), 0u);
-  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
-  for (uint32_t i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
-  return ZKP_OK;
-#else
+// The pair sort and the scan are the engine's own kernels (sort.cu).  -DZKP_USE_CUB swaps in cub::DeviceRadixSort /
+// cub::DeviceScan for A/B measurements (profiles/r01_sort_ab.txt).
+#if defined(ZKP_USE_CUB) && !defined(ZKP_EMU)
+static int sort_pairs(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, uint32_t key_bits,
+                      bool descending, uint32_t** kres, uint32_t** vres) {
   size_t tmp = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, (int)key_bits, ctx->stream);
+  cudaError_t e = descending ? cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, k0, k1, v0, v1, (int)n, 0, (int)key_bits, ctx->stream)
+                             : cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, (int)n, 0, (int)key_bits, ctx->stream);
   if (e != cudaSuccess) return rt::wrap(e);
   ZKP_TRY(ctx->msm.sort_tmp.reserve(tmp));
   tmp = ctx->msm.sort_tmp.cap;
-  e = cub::DeviceRadixSort::SortPairs(ctx->msm.sort_tmp.p, tmp, kin, kout, vin, vout, (int)n, 0, (int)key_bits, ctx->stream);
+  e = descending ? cub::DeviceRadixSort::SortPairsDescending(ctx->msm.sort_tmp.p, tmp, k0, k1, v0, v1, (int)n, 0, (int)key_bits, ctx->stream)
+                 : cub::DeviceRadixSort::SortPairs(ctx->msm.sort_tmp.p, tmp, k0, k1, v0, v1, (int)n, 0, (int)key_bits, ctx->stream);
+  *kres = k1;
+  *vres = v1;
   return rt::wrap(e);
-#endif
 }
-
-// order[] = task ids sorted by run length, longest first
-static int sort_tasks_desc(Ctx* ctx, const uint32_t* len_in, uint32_t* len_out, const uint32_t* id_in, uint32_t* id_out,
-                           uint32_t n, uint32_t key_bits) {
-#ifdef ZKP_EMU
-  (void)ctx; (void)key_bits;
-  std::vector<uint32_t> idx(n);
-  std::iota(idx.begin(), idx.end(), 0u);
-  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return len_in[a] > len_in[b]; });
-  for (uint32_t i = 0; i < n; i++) { len_out[i] = len_in[idx[i]]; id_out[i] = id_in[idx[i]]; }
-  return ZKP_OK;
-#else
-  size_t tmp = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, len_in, len_out, id_in, id_out, (int)n, 0,
-                                                            (int)key_bits, ctx->stream);
-  if (e != cudaSuccess) return rt::wrap(e);
-  ZKP_TRY(ctx->msm.sort_tmp.reserve(tmp));
-  tmp = ctx->msm.sort_tmp.cap;
-  e = cub::DeviceRadixSort::SortPairsDescending(ctx->msm.sort_tmp.p, tmp, len_in, len_out, id_in, id_out, (int)n, 0,
-                                                (int)key_bits, ctx->stream);
-  return rt::wrap(e);
-#endif
-}
-
 static int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
-#ifdef ZKP_EMU
-  (void)ctx;
-  uint32_t acc = 0;
-  for (uint32_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
-  return ZKP_OK;
-#else
   size_t tmp = 0;
   cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, ctx->stream);
   if (e != cudaSuccess) return rt::wrap(e);
@@ -432,8 +401,35 @@ static int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint3
   tmp = ctx->msm.sort_tmp.cap;
   e = cub::DeviceScan::ExclusiveSum(ctx->msm.sort_tmp.p, tmp, in, out, (int)n, ctx->stream);
   return rt::wrap(e);
-#endif
 }
+#elif defined(ZKP_EMU)
+// Emulated build: the radix-sort kernels are exercised directly (tests/test_sort.py); inside the MSM pipeline the
+// emulator groups with std::stable_sort -- the same stable order -- because a ballot costs two OS-thread barriers there.
+static int sort_pairs(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, uint32_t key_bits,
+                      bool descending, uint32_t** kres, uint32_t** vres) {
+  (void)ctx;
+  const uint32_t mask = key_bits >= 32 ? 0xffffffffu : ((1u << key_bits) - 1u);
+  std::vector<uint32_t> idx(n);
+  std::iota(idx.begin(), idx.end(), 0u);
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+    return descending ? (k0[a] & mask) > (k0[b] & mask) : (k0[a] & mask) < (k0[b] & mask);
+  });
+  for (uint32_t i = 0; i < n; i++) { k1[i] = k0[idx[i]]; v1[i] = v0[idx[i]]; }
+  *kres = k1;
+  *vres = v1;
+  return ZKP_OK;
+}
+#else
+static int sort_pairs(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, uint32_t key_bits,
+                      bool descending, uint32_t** kres, uint32_t** vres) {
+  return radix_sort_pairs_dev(ctx, k0, v0, k1, v1, n, key_bits, descending, kres, vres);
+}
+#endif
+#if !(defined(ZKP_USE_CUB) && !defined(ZKP_EMU))
+static int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
+  return scan_exclusive_u32_dev(ctx, in, out, n);
+}
+#endif
 
 static void phase_mark(Ctx* ctx, int i) {
 #ifndef ZKP_EMU
@@ -559,8 +555,9 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   }
   phase_mark(ctx, 1);
   // 2. one sort of every (bucket, point) pair by global bucket id
-  ZKP_TRY(sort_window(ctx, keys_a, keys_b, vals_a, vals_b, (uint32_t)total, key_bits));
-  ctx->msm_launches += (key_bits + 7) / 8 + 1;
+  uint32_t *skeys = nullptr, *svals = nullptr;
+  ZKP_TRY(sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, (uint32_t)total, key_bits, false, &skeys, &svals));
+  ctx->msm_launches += 4 * ((key_bits + 7) / 8);
   phase_mark(ctx, 2);
   // 3. boundaries
   ZKP_TRY(rt::dev_memset(bstart, 0, (size_t)total_buckets * 4, st));
@@ -569,7 +566,8 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    ZKP_LAUNCH_NOSYNC(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, keys_b, total, total_buckets, bstart, bend);
+    ZKP_LAUNCH_NOSYNC(msm_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const uint32_t*)skeys, total, total_buckets,
+                      bstart, bend);
     ctx->msm_launches++;
   }
   // 4. tasks
@@ -589,9 +587,10 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   if (ntasks) {
     uint32_t len_bits = 1;
     while ((1u << len_bits) <= smax) len_bits++;
-    ZKP_TRY(sort_tasks_desc(ctx, task_len, task_len_sorted, task_id, task_order, ntasks, len_bits));
+    uint32_t *len_sorted = nullptr, *order = nullptr;
+    ZKP_TRY(sort_pairs(ctx, task_len, task_id, task_len_sorted, task_order, ntasks, len_bits, true, &len_sorted, &order));
     ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
-               task_order, ntasks, vals_b, bases, partials);
+               (const uint32_t*)order, ntasks, (const uint32_t*)svals, bases, partials);
     ctx->msm_launches += 3;
   }
   // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
@@ -688,6 +687,8 @@ void msm_destroy(Ctx* ctx) {
     if (ctx->phase_ev[i]) { cudaEventDestroy((cudaEvent_t)ctx->phase_ev[i]); ctx->phase_ev[i] = nullptr; }
 #endif
   MsmScratch& m = ctx->msm;
+  ctx->sort_scan.release();
+  ctx->sort_hist.release();
   DevBuf* all[] = {&m.scalars, &m.bases, &m.keys_a, &m.keys_b, &m.vals_a, &m.vals_b, &m.sort_tmp, &m.bucket_start,
                    &m.bucket_end, &m.task_meta, &m.partials, &m.seg_out, &m.win_out, &m.misc};
   for (DevBuf* b : all) b->release();
