@@ -21,7 +21,10 @@ static constexpr uint32_t RS_THREADS = 64;   // emulated build: one OS thread pe
 static constexpr uint32_t RS_THREADS = 256;
 #endif
 static constexpr uint32_t RS_WARPS = RS_THREADS / 32;
-static constexpr uint32_t RS_ITEMS = 16;                       // pairs per thread
+#ifndef ZKP_RS_ITEMS
+#define ZKP_RS_ITEMS 16
+#endif
+static constexpr uint32_t RS_ITEMS = ZKP_RS_ITEMS;             // pairs per thread
 static constexpr uint32_t RS_TILE = RS_THREADS * RS_ITEMS;     // pairs per block
 static constexpr uint32_t RS_DIGITS = 256;
 static constexpr uint32_t SCAN_THREADS = RS_THREADS;
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
   __shared__ uint32_t wcnt[RS_WARPS][RS_DIGITS];  // per-warp digit counts, then the warp's first slot inside the digit
   __shared__ uint32_t dstart[RS_DIGITS];          // first tile slot of every digit
   __shared__ uint32_t scan_tmp[2][RS_THREADS];
-  __shared__ uint32_t skey[RS_TILE], sval[RS_TILE];
+  ZKP_DYN_SMEM(uint32_t, skey);  // RS_TILE keys, then RS_TILE values
+  uint32_t* sval = skey + RS_TILE;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t base = (size_t)blockIdx.x * RS_TILE;
   const uint32_t count = (n - base < RS_TILE) ? (uint32_t)(n - base) : RS_TILE;
@@ -238,6 +242,10 @@ int radix_sort_pairs_dev(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uin
   if (hist_n >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
   ZKP_TRY(ctx->sort_hist.reserve(hist_n * sizeof(uint32_t)));
   uint32_t* hist = ctx->sort_hist.as<uint32_t>();
+  if (!ctx->sort_ready) {
+    ZKP_TRY(rt::allow_smem((const void*)radix_scatter_kernel, 2 * RS_TILE * sizeof(uint32_t)));
+    ctx->sort_ready = true;
+  }
   const uint32_t flip = descending ? 0xffffffffu : 0u;
   uint32_t *kin = k0, *vin = v0, *kout = k1, *vout = v1;
   for (uint32_t shift = 0; shift < key_bits; shift += 8) {
@@ -247,7 +255,7 @@ int radix_sort_pairs_dev(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uin
     ZKP_LAUNCH(radix_hist_kernel, dim3(ntiles), dim3(RS_THREADS), 0, ctx->stream, (const uint32_t*)kin, n, shift, mask, flip,
                ntiles, hist);
     ZKP_TRY(scan_exclusive_u32_dev(ctx, hist, hist, digits * ntiles));
-    ZKP_LAUNCH(radix_scatter_kernel, dim3(ntiles), dim3(RS_THREADS), 0, ctx->stream, (const uint32_t*)kin,
+    ZKP_LAUNCH(radix_scatter_kernel, dim3(ntiles), dim3(RS_THREADS), 2 * RS_TILE * sizeof(uint32_t), ctx->stream, (const uint32_t*)kin,
                (const uint32_t*)vin, kout, vout, n, shift, mask, flip, ntiles, (const uint32_t*)hist);
     uint32_t* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;
