@@ -81,6 +81,7 @@ struct Ctx {
   static constexpr uint32_t EVAL_SLOTS = 16;
   static constexpr uint32_t EVAL_PARTIALS = 4096;  // blocks of 256 x 32 coefficients: up to 2^25 coefficients
   DevBuf poly_scratch, eval_out, eval_partials;
+  uint32_t sort_launches = 0;   // kernels launched by sort.cu since the caller last cleared it
   bool sort_ready = false;      // dynamic shared memory of the scatter kernel opted in
   DevBuf sort_scan, sort_hist;  // sort.cu: tile sums of the u32 scan; digit histograms / offsets [digit][tile]
 

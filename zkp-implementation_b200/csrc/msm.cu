@@ -470,6 +470,7 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars, const G1Affine* bases, size_t n, G1
 int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_list, uint32_t count, const G1Affine* bases,
                       G1Xyzz* out_host, uint32_t fixed_c, size_t table_stride) {
   ctx->msm_launches = 0;
+  ctx->sort_launches = 0;
   const bool fixed = fixed_c != 0;
   if (count == 0) return ZKP_OK;
   if (!fixed && count != 1) return ZKP_ERR_INVALID_ARG;
@@ -557,7 +558,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   // 2. one sort of every (bucket, point) pair by global bucket id
   uint32_t *skeys = nullptr, *svals = nullptr;
   ZKP_TRY(sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, (uint32_t)total, key_bits, false, &skeys, &svals));
-  ctx->msm_launches += 4 * ((key_bits + 7) / 8);
+
   phase_mark(ctx, 2);
   // 3. boundaries
   ZKP_TRY(rt::dev_memset(bstart, 0, (size_t)total_buckets * 4, st));
@@ -578,7 +579,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(exclusive_scan_u32(ctx, ntask, task_off, total_buckets + 1));
   ZKP_LAUNCH_NOSYNC(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
              total_buckets, smax, tasks, task_len, task_id);
-  ctx->msm_launches += 3;
+  ctx->msm_launches += 2;
   uint32_t ntasks = 0;
   ZKP_TRY(rt::d2h(&ntasks, task_off + total_buckets, 4, st));
   ZKP_TRY(rt::sync(st));
@@ -591,7 +592,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     ZKP_TRY(sort_pairs(ctx, task_len, task_id, task_len_sorted, task_order, ntasks, len_bits, true, &len_sorted, &order));
     ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
                (const uint32_t*)order, ntasks, (const uint32_t*)svals, bases, partials);
-    ctx->msm_launches += 3;
+    ctx->msm_launches += 1;
   }
   // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
   phase_mark(ctx, 4);
@@ -627,6 +628,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     ctx->msm_launches += 3;
   }
   phase_mark(ctx, 5);
+  ctx->msm_launches += ctx->sort_launches;  // pair sort, task sort, task-offset scan
   ZKP_TRY(rt::check_last());
   // 7. host: Horner over the window sums (windowed mode); in fixed-base mode set j IS the result of MSM j
   std::vector<G1Xyzz> wins(nsets);

@@ -86,9 +86,11 @@ static int scan_u32_rec(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n,
   const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   ZKP_LAUNCH(scan_u32_tile_kernel, dim3(tiles), dim3(SCAN_THREADS), 0, ctx->stream, in, out, n,
              tiles > 1 ? scratch : (uint32_t*)nullptr);
+  ctx->sort_launches++;
   if (tiles > 1) {
     ZKP_TRY(scan_u32_rec(ctx, scratch, scratch, tiles, scratch + tiles));
     ZKP_LAUNCH_NOSYNC(scan_u32_add_kernel, dim3(tiles), dim3(SCAN_THREADS), 0, ctx->stream, out, n, (const uint32_t*)scratch);
+    ctx->sort_launches++;
   }
   return ZKP_OK;
 }
@@ -257,6 +259,7 @@ int radix_sort_pairs_dev(Ctx* ctx, uint32_t* k0, uint32_t* v0, uint32_t* k1, uin
     ZKP_TRY(scan_exclusive_u32_dev(ctx, hist, hist, digits * ntiles));
     ZKP_LAUNCH(radix_scatter_kernel, dim3(ntiles), dim3(RS_THREADS), 2 * RS_TILE * sizeof(uint32_t), ctx->stream, (const uint32_t*)kin,
                (const uint32_t*)vin, kout, vout, n, shift, mask, flip, ntiles, (const uint32_t*)hist);
+    ctx->sort_launches += 2;
     uint32_t* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;
   }
