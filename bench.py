@@ -294,7 +294,7 @@ def run_engine(args) -> None:
             "bound": "hbm", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
             "frac": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
             "algorithmic_bytes": ntt_bytes, "passes_counted": passes_min, "passes_run": eng.last_launches("ntt"),
-            "traffic": None,
+            "traffic": ntt_traffic(eng.last_launches("ntt")),
             "integer_bound_note": "butterfly arithmetic = N/2*log2(N)*136 IMAD; fraction of the measured IMAD.WIDE peak below",
             "int_pipe_frac": ntt_imad / (ntt_ms * 1e-3) / imad_wide if imad_wide else None,
         }
@@ -376,6 +376,14 @@ def plonk_and_2p20(z, eng, torch, scalars):
     out["plonk_proof_sha256"] = digest
     out["plonk_config"] = "chain circuit, 2^20 - 3 gates (alternating mul / add, c_i wired to a_(i+1)), seed 20, fixed b1..b9"
     return out
+
+
+def ntt_traffic(passes):
+    """DRAM bytes of one 2^24 transform = passes x the per-launch figure of the committed ncu capture."""
+    tp = os.path.join(ROOT, "profiles", "ntt_pass_traffic.json")
+    if not os.path.exists(tp):
+        return None
+    return json.load(open(tp)).get("dram_bytes_per_launch", 0) * passes
 
 
 def timed_local(torch, fn, steps, warmup):
