@@ -171,7 +171,9 @@ class CompiledCircuit:
 
     def close(self) -> None:
         if self._h:
-            self.engine.lib.zkp_plonk_compiled_free(self._h)
+            # the native object frees its device buffers through the context: only while the engine is still open
+            if getattr(self.engine, "_h", None):
+                self.engine.lib.zkp_plonk_compiled_free(self._h)
             self._h = None
 
     def __del__(self):
