@@ -27,6 +27,28 @@ static void write_affine(const G1Xyzz& p, uint64_t out_xy[12], uint8_t* out_inf)
   if (out_inf) *out_inf = a.is_inf() ? 1 : 0;
 }
 
+// count results normalised with ONE Fq inversion (Montgomery's trick over the ZZ * ZZZ of the finite entries)
+static void write_affine_batch(const G1Xyzz* p, uint32_t count, uint64_t* out_xy, uint8_t* out_inf) {
+  std::vector<Fq> pre(count);
+  Fq prod = Fq::one();
+  for (uint32_t i = 0; i < count; i++) {
+    pre[i] = prod;
+    if (!p[i].is_inf()) prod = prod * (p[i].zz * p[i].zzz);
+  }
+  Fq inv = fp_inv(prod);
+  for (uint32_t i = count; i-- > 0;) {
+    G1Affine a = G1Affine::infinity();
+    if (!p[i].is_inf()) {
+      const Fq ti = inv * pre[i];  // (zz * zzz)^-1
+      inv = inv * (p[i].zz * p[i].zzz);
+      a.x = p[i].x * (ti * p[i].zzz);  // X / ZZ
+      a.y = p[i].y * (ti * p[i].zz);   // Y / ZZZ
+    }
+    memcpy(out_xy + 12 * (size_t)i, &a, sizeof(a));
+    if (out_inf) out_inf[i] = a.is_inf() ? 1 : 0;
+  }
+}
+
 extern "C" {
 
 const char* zkp_strerror(int status) {
@@ -77,6 +99,7 @@ void zkp_ctx_destroy(zkp_ctx* h) {
   msm_destroy(&h->c);
   rt::dev_free(h->c.srs);
   rt::dev_free(h->c.srs_tab);
+  rt::dev_free(h->c.srs0_tab);
 #ifndef ZKP_EMU
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
 #endif
@@ -143,8 +166,10 @@ static int stage_affine(Ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n
 static int srs_alloc(Ctx* c, size_t n) {
   rt::dev_free(c->srs);
   rt::dev_free(c->srs_tab);
+  rt::dev_free(c->srs0_tab);
   c->srs = nullptr;
   c->srs_tab = nullptr;
+  c->srs0_tab = nullptr;
   c->srs_tab_c = 0;
   c->srs_len = 0;
   ZKP_TRY(rt::dev_malloc((void**)&c->srs, n * sizeof(G1Affine)));
@@ -252,7 +277,7 @@ int zkp_msm_g1_multi_dev(zkp_ctx* h, uint32_t count, const void* const* scalars_
     }
     c->msm_launches = launches;
   }
-  for (uint32_t j = 0; j < count; j++) write_affine(acc[j], out_xy + 12 * j, out_infinity ? out_infinity + j : nullptr);
+  write_affine_batch(acc, count, out_xy, out_infinity);
   return ZKP_OK;
 }
 
@@ -570,8 +595,8 @@ int zkp_g1_mul_srs0(zkp_ctx* h, const uint64_t* scalars, uint32_t count, uint64_
   if (count > 64 || (count && (!scalars || !out_xy))) return ZKP_ERR_INVALID_ARG;
   if (count && c->srs_len == 0) return ZKP_ERR_SRS_TOO_SMALL;
   G1Xyzz tmp[64];
-  ZKP_TRY(g1_scalar_mul_dev(c, c->srs, (const Fr*)scalars, count, tmp));
-  for (uint32_t k = 0; k < count; k++) write_affine(tmp[k], out_xy + 12 * k, nullptr);
+  ZKP_TRY(g1_scalar_mul_dev(c, (const Fr*)scalars, count, tmp));
+  write_affine_batch(tmp, count, out_xy, nullptr);
   return ZKP_OK;
 }
 

@@ -69,6 +69,7 @@ struct Ctx {
   // fixed-base table over the SRS (zkp_srs_precompute): window w = 2^(c w) * srs[i], w < srs_tab_windows
   G1Affine* srs_tab = nullptr;
   uint32_t srs_tab_c = 0, srs_tab_windows = 0;
+  G1Affine* srs0_tab = nullptr;  // 32 x 256 byte-window table of srs[0] for commit_para (built on first use)
 
   // NTT state
   Fr* w_fwd = nullptr;  // omega_{2^WLOG}^i, i < 2^(WLOG-1)

@@ -405,21 +405,75 @@ int plonk_gate_check_dev(Ctx* ctx, const Fr* const cols[9], size_t n, bool* ok) 
 }
 
 // ---- k * P for a few scalars (commit_para) --------------------------------------------------------
-__global__ void g1_scalar_mul_kernel(const G1Affine* base, const Fr* scalars, uint32_t count, G1Xyzz* out) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const Fr k = fp_from_mont(ld_fr(scalars + t));  // `into_bigint()` inside ark-ec's scalar mul
-  st_xyzz(out + t, xyzz_mul_limbs(G1Xyzz::from_affine(ld_affine(base)), k.v, 8));
+// The base is always srs[0]: a 32 x 256 window table d * 2^(8w) * P (built once per SRS) turns k * P into 32
+// table entries, one per byte of the canonical scalar, summed by a warp.
+static constexpr uint32_t PTAB_WINDOWS = 32, PTAB_DIGITS = 256;
+
+__global__ void g1_base_table_kernel(const G1Affine* base, G1Xyzz* tab) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= PTAB_WINDOWS) return;
+  G1Xyzz b = G1Xyzz::from_affine(ld_affine(base));
+  for (uint32_t k = 0; k < 8 * w; k++) b = xyzz_dbl(b);
+  G1Xyzz acc = G1Xyzz::infinity();
+  for (uint32_t d = 0; d < PTAB_DIGITS; d++) {
+    st_xyzz(tab + (size_t)w * PTAB_DIGITS + d, acc);
+    xyzz_add(acc, b);
+  }
 }
 
-int g1_scalar_mul_dev(Ctx* ctx, const G1Affine* base_dev, const Fr* scalars_host, uint32_t count, G1Xyzz* out_host) {
+// one block of 32 threads per scalar: lane w contributes table[w][byte w of k]
+__global__ void __launch_bounds__(32) g1_scalar_mul_kernel(const G1Affine* __restrict__ tab, const Fr* scalars, uint32_t count,
+                                                           G1Xyzz* out) {
+  __shared__ G1Xyzz sh[32];
+  const uint32_t t = blockIdx.x, w = threadIdx.x;
+  if (t >= count) return;
+  const Fr k = fp_from_mont(ld_fr(scalars + t));  // `into_bigint()` inside ark-ec's scalar mul
+  const uint32_t d = (k.v[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+  G1Xyzz acc = G1Xyzz::infinity();
+  if (d) acc = G1Xyzz::from_affine(ld_affine(tab + (size_t)w * PTAB_DIGITS + d));
+  st_xyzz(&sh[w], acc);
+  __syncthreads();
+  for (uint32_t s = 16; s > 0; s >>= 1) {
+    if (w < s) {
+      G1Xyzz a = ld_xyzz(&sh[w]), b = ld_xyzz(&sh[w + s]);
+      xyzz_add(a, b);
+      st_xyzz(&sh[w], a);
+    }
+    __syncthreads();
+  }
+  if (w == 0) st_xyzz(out + t, ld_xyzz(&sh[0]));
+}
+
+int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out);  // gen.cu
+
+// scalars[k] * srs[0] for count <= 64 scalars (host in, host XYZZ out)
+int g1_scalar_mul_dev(Ctx* ctx, const Fr* scalars_host, uint32_t count, G1Xyzz* out_host) {
   if (!count) return ZKP_OK;
-  if (count > 64) return ZKP_ERR_INVALID_ARG;
+  if (count > 64 || ctx->srs_len == 0) return ZKP_ERR_INVALID_ARG;
+  const size_t tab_n = (size_t)PTAB_WINDOWS * PTAB_DIGITS;
+  if (!ctx->srs0_tab) {  // first commit_para against this SRS
+    DevBuf tmp;
+    ZKP_TRY(tmp.reserve(tab_n * sizeof(G1Xyzz)));
+    int st = rt::dev_malloc((void**)&ctx->srs0_tab, tab_n * sizeof(G1Affine));
+    if (st == ZKP_OK) {
+      ZKP_LAUNCH_NOSYNC(g1_base_table_kernel, dim3(1), dim3(PTAB_WINDOWS), 0, ctx->stream, (const G1Affine*)ctx->srs,
+                        tmp.as<G1Xyzz>());
+      st = normalise_dev(ctx, tmp.as<G1Xyzz>(), tab_n, ctx->srs0_tab);
+    }
+    if (st == ZKP_OK) st = rt::sync(ctx->stream);
+    tmp.release();
+    if (st != ZKP_OK) {
+      rt::dev_free(ctx->srs0_tab);
+      ctx->srs0_tab = nullptr;
+      return st;
+    }
+  }
   ZKP_TRY(ctx->eval_partials.reserve(Ctx::EVAL_SLOTS * Ctx::EVAL_PARTIALS * sizeof(Fr)));
   Fr* ds = ctx->eval_partials.as<Fr>();
   G1Xyzz* dout = reinterpret_cast<G1Xyzz*>(ds + 64);
   ZKP_TRY(rt::h2d(ds, scalars_host, count * sizeof(Fr), ctx->stream));
-  ZKP_LAUNCH_NOSYNC(g1_scalar_mul_kernel, dim3(count), dim3(1), 0, ctx->stream, base_dev, (const Fr*)ds, count, dout);
+  ZKP_LAUNCH(g1_scalar_mul_kernel, dim3(count), dim3(32), 0, ctx->stream, (const G1Affine*)ctx->srs0_tab, (const Fr*)ds, count,
+             dout);
   ZKP_TRY(rt::d2h(out_host, dout, count * sizeof(G1Xyzz), ctx->stream));
   ZKP_TRY(rt::sync(ctx->stream));
   return rt::check_last();

@@ -49,6 +49,6 @@ int fr_trimmed_len_dev(Ctx* ctx, const Fr* coeffs, size_t n, size_t* out_len);
 int plonk_numden_dev(Ctx* ctx, const PlonkNumDenArgs& p);
 int plonk_quotient_dev(Ctx* ctx, const PlonkQuotientArgs& p);
 int plonk_gate_check_dev(Ctx* ctx, const Fr* const cols[9], size_t n, bool* ok);
-int g1_scalar_mul_dev(Ctx* ctx, const G1Affine* base_dev, const Fr* scalars_host, uint32_t count, G1Xyzz* out_host);
+int g1_scalar_mul_dev(Ctx* ctx, const Fr* scalars_host, uint32_t count, G1Xyzz* out_host);  // scalars[k] * srs[0]
 
 }  // namespace zkp
