@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(RED_THREADS) msm_pair_add_kernel(const G1Xyzz*
 
 // A_l partial sums: block (bx, y = l * nsets + w) sums a chunk of the odd entries of X^l of set w
 struct RedLevels {
-  uint32_t off[MAX_RED_LEVELS];  // element offset of X^l (layout [set][m_l])
-  uint32_t m[MAX_RED_LEVELS];    // entries per set at level l
+  uint32_t off[MAX_RED_LEVELS + 1];  // element offset of X^l (layout [set][m_l]); off[levels] = X^levels (one entry per set)
+  uint32_t m[MAX_RED_LEVELS + 1];    // entries per set at level l
 };
 static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (level, set) for the largest level
 static constexpr uint32_t SUM_MIN_CHUNK = 16 * RED_THREADS;  // >= 16 serial additions per thread ahead of the 7-step tree
@@ -288,6 +288,27 @@ __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz
     __syncthreads();
   }
   if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz(&sh[0]));
+}
+
+// The last levels (<= TAIL_M entries per set) in ONE launch: block w walks set w's remaining levels, one
+// __syncthreads between levels instead of one launch per level (a level is a single addition deep).
+static constexpr uint32_t TAIL_M = 8 * RED_THREADS;
+
+__global__ void __launch_bounds__(RED_THREADS) msm_pair_tail_kernel(G1Xyzz* __restrict__ buf, RedLevels lv, uint32_t l0,
+                                                                    uint32_t levels) {
+  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  for (uint32_t l = l0; l < levels; l++) {
+    const uint32_t m = lv.m[l];
+    const G1Xyzz* in = buf + lv.off[l] + (size_t)w * m;
+    G1Xyzz* out = buf + lv.off[l + 1] + (size_t)w * (m >> 1);
+    for (uint32_t i = tid; i < (m >> 1); i += blockDim.x) {
+      G1Xyzz a = ld_xyzz(in + 2 * (size_t)i);
+      const G1Xyzz b = ld_xyzz(in + 2 * (size_t)i + 1);
+      xyzz_add(a, b);
+      st_xyzz(out + i, a);
+    }
+    __syncthreads();
+  }
 }
 
 // stage 2: A[y] = sum of the stage-1 partials of (level, set) y (layout [y][chunks])
@@ -607,15 +628,22 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     RedLevels lv;
     memset(&lv, 0, sizeof(lv));
     size_t off = 0;
-    for (uint32_t l = 0; l < levels; l++) {
-      const uint32_t mm = nbuckets >> l;
+    for (uint32_t l = 0; l <= levels; l++) {
       lv.off[l] = (uint32_t)off;
-      lv.m[l] = mm;
-      const uint32_t pairs = (mm >> 1) * nsets;
+      lv.m[l] = nbuckets >> l;
+      off += (size_t)(nbuckets >> l) * nsets;
+    }
+    off = lv.off[levels];
+    uint32_t l = 0;
+    for (; l < levels && lv.m[l] > TAIL_M; l++) {  // wide levels: one launch each
+      const uint32_t pairs = (lv.m[l] >> 1) * nsets;
       ZKP_LAUNCH_NOSYNC(msm_pair_add_kernel, dim3((pairs + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
-                 (const G1Xyzz*)(lvl_buf + off), pairs, lvl_buf + off + (size_t)mm * nsets);
+                 (const G1Xyzz*)(lvl_buf + lv.off[l]), pairs, lvl_buf + lv.off[l + 1]);
       ctx->msm_launches++;
-      off += (size_t)mm * nsets;
+    }
+    if (l < levels) {  // the rest in one launch, one block per set
+      ZKP_LAUNCH(msm_pair_tail_kernel, dim3(nsets), dim3(RED_THREADS), 0, st, lvl_buf, lv, l, levels);
+      ctx->msm_launches++;
     }
     // A_l = sum of the odd entries of X^l, every level and set in one launch; the combine finishes the sums
     G1Xyzz* plane = sum_scratch + (size_t)chunks * levels * nsets;  // [levels * nsets]
