@@ -99,7 +99,11 @@ class KzgScheme:
         self.srs = srs
         engine.srs_upload(srs.g1_limbs())
         if precompute and len(srs):
-            engine.srs_precompute()  # fixed-base table: one bucket set for all windows of every commit
+            try:
+                engine.srs_precompute()  # fixed-base table: one bucket set for all windows of every commit
+            except Exception as ex:  # the table is an accelerator (12 x the SRS in HBM): without room for it
+                if getattr(ex, "status", None) != 3:  # ZKP_B200_ERR_OOM -> the windowed GPU path serves the commits
+                    raise
 
     # scheme.rs:84-96
     def _evaluate_in_s(self, coeffs: Sequence[int]) -> Point:
