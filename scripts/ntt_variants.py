@@ -5,11 +5,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
-    "mb3": ["-DNTT_MIN_BLOCKS=3"],
-    "t10_mb4": ["-DNTT_TILE_LOG=10", "-DNTT_MIN_BLOCKS=4"],
-    "t10_mb3": ["-DNTT_TILE_LOG=10", "-DNTT_MIN_BLOCKS=3"],
-    "t12_th512_mb1": ["-DNTT_TILE_LOG=12", "-DNTT_THREADS_PER_CTA=512", "-DNTT_MIN_BLOCKS=1"],
-    "t11_th128_mb4": ["-DNTT_THREADS_PER_CTA=128", "-DNTT_MIN_BLOCKS=3"],
+    "p2_t12_th512": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=512", "-DNTT_MIN_BLOCKS=1"],
+    "p2_t12_th256": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=256", "-DNTT_MIN_BLOCKS=1"],
+    "p2_t12_th1024": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=1024", "-DNTT_MIN_BLOCKS=1"],
+    "r10_t11": ["-DNTT_RMAX=10"],
+    "r11_t11": ["-DNTT_RMAX=11"],
 }
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "zkp-implementation_b200", "build.py"))

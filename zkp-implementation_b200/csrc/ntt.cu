@@ -21,8 +21,14 @@
 
 namespace zkp {
 
-static constexpr uint32_t WLOG = 11;       // sub-transform twiddle table: omega_{2^11}^i, i < 2^10
-static constexpr uint32_t RMAX = 9;        // largest digit of a multi-pass schedule
+#ifndef NTT_WLOG
+#define NTT_WLOG 11
+#endif
+#ifndef NTT_RMAX
+#define NTT_RMAX 10
+#endif
+static constexpr uint32_t WLOG = NTT_WLOG;  // sub-transform twiddle table: omega_{2^11}^i, i < 2^10
+static constexpr uint32_t RMAX = NTT_RMAX;  // largest digit of a multi-pass schedule
 #ifndef NTT_TILE_LOG
 #define NTT_TILE_LOG 11
 #endif
