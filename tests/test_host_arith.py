@@ -26,7 +26,8 @@ def test_field_ops(hostlib, zkp, name):
     cases += [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(1500)]
     out = (ctypes.c_uint32 * n)()
     for a, b in cases:
-        for op, exp in ((0, (a + b) % mod), (1, (a - b) % mod), (2, a * b * rinv % mod), (3, a * b * rinv % mod)):
+        for op, exp in ((0, (a + b) % mod), (1, (a - b) % mod), (2, a * b * rinv % mod), (3, a * b * rinv % mod),
+                        (7, a * b * rinv % mod)):
             assert fn(op, _pack(a, n), _pack(b, n), out) == 0
             assert _unpack(out) == exp, (name, op, hex(a), hex(b))
     a = rnd.randrange(1, mod)

@@ -245,6 +245,58 @@ ZKP_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---- 64-bit-limb CIOS for the host pass (finishing arithmetic of every MSM, the CPU kernel emulator) ---------
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+#define ZKP_HOST_MUL64 1
+template <class P>
+inline Fp<P> fp_mul_host64(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int M = P::N / 2;
+  static_assert(P::N % 2 == 0, "even limb count");
+  typedef unsigned __int128 u128;
+  uint64_t x[M], y[M], p[M], t[M + 2];
+  for (int i = 0; i < M; i++) {
+    x[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    y[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+    p[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+    t[i] = 0;
+  }
+  t[M] = t[M + 1] = 0;
+  // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
+  uint64_t pinv = (uint64_t)(0u - P::M0);      // p^-1 mod 2^32
+  pinv = pinv * (2 - p[0] * pinv);             // mod 2^64
+  const uint64_t ninv = 0 - pinv;
+  for (int i = 0; i < M; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < M; j++) {
+      const u128 uv = (u128)x[j] * y[i] + t[j] + c;
+      t[j] = (uint64_t)uv;
+      c = (uint64_t)(uv >> 64);
+    }
+    u128 s2 = (u128)t[M] + c;
+    t[M] = (uint64_t)s2;
+    t[M + 1] = (uint64_t)(s2 >> 64);
+    const uint64_t m = t[0] * ninv;
+    u128 uv = (u128)m * p[0] + t[0];
+    c = (uint64_t)(uv >> 64);
+    for (int j = 1; j < M; j++) {
+      uv = (u128)m * p[j] + t[j] + c;
+      t[j - 1] = (uint64_t)uv;
+      c = (uint64_t)(uv >> 64);
+    }
+    s2 = (u128)t[M] + c;
+    t[M - 1] = (uint64_t)s2;
+    t[M] = t[M + 1] + (uint64_t)(s2 >> 64);
+  }
+  Fp<P> r;
+  for (int i = 0; i < M; i++) {
+    r.v[2 * i] = (uint32_t)t[i];
+    r.v[2 * i + 1] = (uint32_t)(t[i] >> 32);
+  }
+  fp_final_sub(r);  // t < 2p and both moduli leave spare top bits, so t[M] == 0 here
+  return r;
+}
+#endif
+
 // ---- even/odd carry-chain Montgomery product (device path) ---------------------------------------
 #if defined(__CUDACC__)
 // 0xffffffff read from the constant bank at run time: keeps ptxas from treating m = -t0 as a negation
@@ -372,6 +424,8 @@ template <class P>
 ZKP_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if ZKP_PTX_DEVICE || defined(ZKP_FIELD_CHAIN_ON_HOST)
   return fp_mul_chain(a, b);
+#elif defined(ZKP_HOST_MUL64) && !defined(ZKP_FIELD_PORTABLE)
+  return fp_mul_host64(a, b);
 #else
   return fp_mul_portable(a, b);
 #endif

@@ -10,7 +10,7 @@ using namespace zkp;
 
 extern "C" {
 
-// op: 0 add, 1 sub, 2 mul (portable), 3 mul (carry-chain algorithm), 4 inv, 5 to_mont, 6 from_mont
+// op: 0 add, 1 sub, 2 mul (portable), 3 mul (carry-chain algorithm), 4 inv, 5 to_mont, 6 from_mont, 7 mul (64-bit host CIOS)
 int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   Fr x, y, r;
   memcpy(x.v, a, 32);
@@ -23,6 +23,7 @@ int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 4: r = fp_inv(x); break;
     case 5: r = fp_to_mont(x); break;
     case 6: r = fp_from_mont(x); break;
+    case 7: r = fp_mul_host64(x, y); break;
     default: return 1;
   }
   memcpy(out, r.v, 32);
@@ -41,6 +42,7 @@ int zkp_t_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 4: r = fp_inv(x); break;
     case 5: r = fp_to_mont(x); break;
     case 6: r = fp_from_mont(x); break;
+    case 7: r = fp_mul_host64(x, y); break;
     default: return 1;
   }
   memcpy(out, r.v, 48);
