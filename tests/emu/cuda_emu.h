@@ -97,6 +97,20 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   return acc;
 }
 
+static inline unsigned __match_any_sync(unsigned, unsigned value) {
+  // one exchange round: every lane publishes its value, then collects the lanes that published the same one
+  auto* st = zkp_emu::state();
+  const unsigned w = zkp_emu_tid >> 5, lane = zkp_emu_tid & 31;
+  st->warp_slots[w * 32 + lane] = value;
+  pthread_barrier_wait(&st->warp_barriers[w]);
+  const unsigned base = w * 32;
+  const unsigned nl = std::min(32u, st->nthreads - base);
+  unsigned acc = 0;
+  for (unsigned l = 0; l < nl; l++) acc |= (unsigned)(st->warp_slots[base + l] == (uint64_t)value) << l;
+  pthread_barrier_wait(&st->warp_barriers[w]);
+  return acc;
+}
+
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -147,14 +147,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     key[r] = live ? kin[base + i] : 0xffffffffu;
     val[r] = live ? vin[base + i] : 0u;
     const uint32_t d = live ? rs_digit(key[r], shift, mask, flip) : 0u;
-    // lanes holding the same digit (dead lanes match nobody)
-    uint32_t peers = __ballot_sync(0xffffffffu, live);
-#pragma unroll
-    for (uint32_t b = 0; b < 8; b++) {
-      const uint32_t bit = (d >> b) & 1u;
-      const uint32_t vote = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? vote : ~vote;
-    }
+    // lanes holding the same digit (MATCH.ANY); a dead lane gets a value no digit can take, so it matches nobody live
+    const uint32_t peers = __match_any_sync(0xffffffffu, live ? d : (RS_DIGITS + lane));
     const uint32_t before = peers & ((1u << lane) - 1u);
     uint32_t prev = 0;
     if (live) prev = wcnt[warp][d];
