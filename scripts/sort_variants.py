@@ -8,7 +8,7 @@ n = 201326592
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 keys0 = torch.randint(0, 1 << 21, (n,), dtype=torch.int32, device="cuda", generator=g)
 vals0 = torch.arange(n, dtype=torch.int32, device="cuda")
-for name in ("b200", "b200_rs8", "b200_rs12", "b200_rs20"):
+for name in ("b200",):
     path = os.path.join(ROOT, "zkp-implementation_b200", "libzkp_%s.so" % name)
     if not os.path.exists(path):
         continue

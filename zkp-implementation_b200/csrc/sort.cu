@@ -215,11 +215,14 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
   }
   __syncthreads();
 
-  // phase D: runs of equal digits go out to consecutive addresses
+  // phase D: runs of equal digits go out to consecutive addresses; goff[d] = global slot of the digit's first
+  // pair of this tile minus its tile slot, so the output position of tile slot j is goff[d] + j
+  uint32_t* goff = &wcnt[0][0];  // the per-warp counters are dead after phase C
+  for (uint32_t d = tid; d <= mask; d += RS_THREADS) goff[d] = offs[(size_t)d * ntiles + blockIdx.x] - dstart[d];
+  __syncthreads();
   for (uint32_t j = tid; j < count; j += RS_THREADS) {
     const uint32_t k = skey[j];
-    const uint32_t d = rs_digit(k, shift, mask, flip);
-    const uint32_t pos = offs[(size_t)d * ntiles + blockIdx.x] + (j - dstart[d]);
+    const uint32_t pos = goff[rs_digit(k, shift, mask, flip)] + j;
     kout[pos] = k;
     vout[pos] = sval[j];
   }
