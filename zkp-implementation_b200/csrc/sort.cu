@@ -20,6 +20,10 @@ static constexpr uint32_t RS_THREADS = 64;   // emulated build: one OS thread pe
 #else
 static constexpr uint32_t RS_THREADS = 256;
 #endif
+#ifndef ZKP_RS_MIN_BLOCKS
+#define ZKP_RS_MIN_BLOCKS 4
+#endif
+static constexpr uint32_t RS_MIN_BLOCKS = ZKP_RS_MIN_BLOCKS;  // resident scatter blocks per SM (64 registers per thread)
 static constexpr uint32_t RS_WARPS = RS_THREADS / 32;
 #ifndef ZKP_RS_ITEMS
 #define ZKP_RS_ITEMS 16
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
   for (uint32_t d = tid; d <= mask; d += RS_THREADS) hist[(size_t)d * ntiles + blockIdx.x] = cnt[d];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                                    uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                                    uint32_t n, uint32_t shift, uint32_t mask, uint32_t flip,
                                                                    uint32_t ntiles, const uint32_t* __restrict__ offs) {
