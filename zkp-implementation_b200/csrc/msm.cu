@@ -256,7 +256,8 @@ struct RedLevels {
   uint32_t m[MAX_RED_LEVELS + 1];    // entries per set at level l
 };
 static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (level, set) for the largest level
-static constexpr uint32_t SUM_MIN_CHUNK = 16 * RED_THREADS;  // >= 16 serial additions per thread ahead of the 7-step tree
+static constexpr uint32_t SUM_MIN_CHUNK = 2 * RED_THREADS;   // small bucket sets: 2 serial additions per thread ahead of the 7-step tree;
+                                                             // large ones are capped at SUM_CHUNKS blocks, i.e. 16 per thread at 2^21 buckets
 
 __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
                                                                     uint32_t nsets, G1Xyzz* __restrict__ out) {
