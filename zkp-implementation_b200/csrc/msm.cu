@@ -536,8 +536,13 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
+  // stage-1 blocks per (level, set): enough for ~2 waves over all sets at the widest level, never more than one
+  // block per SUM_MIN_CHUNK entries
   uint32_t chunks = ((nbuckets >> 1) + SUM_MIN_CHUNK - 1) / SUM_MIN_CHUNK;
-  if (chunks > SUM_CHUNKS) chunks = SUM_CHUNKS;
+  uint32_t chunk_cap = 1200 / nsets;
+  if (chunk_cap > SUM_CHUNKS) chunk_cap = SUM_CHUNKS;
+  if (chunk_cap < 1) chunk_cap = 1;
+  if (chunks > chunk_cap) chunks = chunk_cap;
   if (chunks < 1) chunks = 1;
   ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + ((size_t)chunks + 1) * (c - 1) * nsets) * sizeof(G1Xyzz)));
   ZKP_TRY(m.win_out.reserve((size_t)(nsets + 1) * sizeof(G1Xyzz)));
