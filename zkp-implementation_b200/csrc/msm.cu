@@ -256,16 +256,18 @@ struct RedLevels {
   uint32_t m[MAX_RED_LEVELS + 1];    // entries per set at level l
 };
 static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (level, set) for the largest level
-static constexpr uint32_t SUM_MIN_CHUNK = 2 * RED_THREADS;   // small bucket sets: 2 serial additions per thread ahead of the 7-step tree;
-                                                             // large ones are capped at SUM_CHUNKS blocks, i.e. 16 per thread at 2^21 buckets
+// entries per stage-1 block: 16 serial additions per thread ahead of the 7-step tree when the sums are throughput-bound
+// (large bucket sets), 2 when they are latency-bound (small ones)
+static constexpr uint32_t SUM_CHUNK_LARGE = 16 * RED_THREADS, SUM_CHUNK_SMALL = 2 * RED_THREADS;
 
 __global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
-                                                                    uint32_t nsets, G1Xyzz* __restrict__ out) {
+                                                                    uint32_t nsets, uint32_t min_chunk,
+                                                                    G1Xyzz* __restrict__ out) {
   __shared__ G1Xyzz sh[RED_THREADS];
   const uint32_t l = blockIdx.y / nsets, w = blockIdx.y - l * nsets, tid = threadIdx.x;
   const uint32_t count = lv.m[l] >> 1;  // odd entries
   uint32_t chunk = (count + gridDim.x - 1) / gridDim.x;
-  if (chunk < SUM_MIN_CHUNK) chunk = SUM_MIN_CHUNK;  // short arrays: fewer, fuller blocks
+  if (chunk < min_chunk) chunk = min_chunk;  // short arrays: fewer, fuller blocks
   const uint32_t lo = blockIdx.x * chunk;
   if (lo >= count) {  // block-uniform: nothing to sum
     if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, G1Xyzz::infinity());
@@ -537,8 +539,9 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
   ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
   // stage-1 blocks per (level, set): enough for ~2 waves over all sets at the widest level, never more than one
-  // block per SUM_MIN_CHUNK entries
-  uint32_t chunks = ((nbuckets >> 1) + SUM_MIN_CHUNK - 1) / SUM_MIN_CHUNK;
+  // block per min_chunk entries
+  const uint32_t min_chunk = ((size_t)nbuckets * nsets <= ((size_t)1 << 17)) ? SUM_CHUNK_SMALL : SUM_CHUNK_LARGE;
+  uint32_t chunks = ((nbuckets >> 1) + min_chunk - 1) / min_chunk;
   uint32_t chunk_cap = 1200 / nsets;
   if (chunk_cap > SUM_CHUNKS) chunk_cap = SUM_CHUNKS;
   if (chunk_cap < 1) chunk_cap = 1;
@@ -654,7 +657,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
     // A_l = sum of the odd entries of X^l, every level and set in one launch; the combine finishes the sums
     G1Xyzz* plane = sum_scratch + (size_t)chunks * levels * nsets;  // [levels * nsets]
     ZKP_LAUNCH(msm_plane_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
-               nsets, sum_scratch);
+               nsets, min_chunk, sum_scratch);
     ZKP_LAUNCH(msm_plane_sum2_kernel, dim3(levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)sum_scratch, chunks,
                plane);
     ZKP_LAUNCH(msm_reduce_combine_kernel, dim3(nsets), dim3(32), 0, st, (const G1Xyzz*)plane, 1u,
