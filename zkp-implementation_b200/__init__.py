@@ -164,6 +164,10 @@ class Engine:
         except Exception:
             pass
 
+    def is_cuda(self) -> bool:
+        """False for the CPU kernel emulator of the test-suite (tests/emu)."""
+        return os.path.basename(getattr(self.lib, "_name", "")) == LIB_NAME
+
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self.lib.zkp_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
 

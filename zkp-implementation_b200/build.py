@@ -76,7 +76,10 @@ def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_na
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
     objs += _host_objs(bdir)
-    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp", "-o", out, *objs])
+    # --cudart shared: the CUDA runtime is resolved from the image (or shared with torch when torch loaded it first)
+    # instead of being embedded in the product library
+    _run([nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",
+          "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", out, *objs])
     return out
 
 
@@ -111,6 +114,6 @@ def build_emu(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["cuda", "hosttest"]
+    what = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cuda", "hosttest"]
     for w in what:
         print(w, "->", {"cuda": build_cuda, "hosttest": build_hosttest, "emu": build_emu}[w](force="--force" in sys.argv))

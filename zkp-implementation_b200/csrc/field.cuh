@@ -13,6 +13,11 @@
 //     register pair and ptxas fuses it into one IMAD.WIDE.U32 with carry-in/out.
 // The PTX primitives have a host emulation (explicit carry flag) so the very same algorithm text is
 // unit-tested on the CPU build before it ever reaches a GPU.
+//
+// Credit: the even/odd two-accumulator carry-chain schedule of the device multiplier (detail::mul_n, cmad_n,
+// madc_n_rshift, mad_n_redc below) follows the public technique of supranational/sppark's `ff/mont_t.cuh`
+// (Apache-2.0); it is re-stated here for this engine's limb containers.  The Fr low-limb reduction
+// (r = 1 mod 2^32), the dedicated squaring, and the host carry-flag emulation are this repository's own.
 #pragma once
 #include <stdint.h>
 

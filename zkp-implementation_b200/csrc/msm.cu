@@ -15,8 +15,9 @@
 //                  list is sorted by run length (longest first) so the 32 lanes of a warp finish together
 //   5. accumulate  one thread per task: XYZZ accumulator += affine base (mixed add, 8M+2S),
 //                  next base prefetched while the current add runs
-//   6. reduce      sum_b (b+1) B_b per bucket set as a base-16 digit recursion: every level is a batch of
-//                  independent 16-element running sums, so even a few thousand buckets fill the GPU
+//   6. reduce      sum_b (b+1) B_b per bucket set by bit planes of the bucket index: level l halves the array
+//                  (one independent addition per thread) and A_l = sum of the odd entries of level l, so the
+//                  serial depth is c - 1 additions however many buckets there are
 //   7. host        windowed mode only: Horner over the W window sums; the caller normalises (one inversion)
 //
 // Two modes.  WINDOWED (ad-hoc bases): window w has its own 2^(c-1) buckets.  FIXED-BASE (the resident SRS

@@ -81,8 +81,19 @@ class DistNtt:
         self.rows_local = (1 << self.r) // world
         self._exch = 0
         self._peers = None
+        self._bind_stream()
         if p2p:
             self._open_peers()
+
+    def _bind_stream(self) -> None:
+        """Stream contract: the engine's kernels (stage, permute, local transforms, copies) and torch's
+        collectives / allocations must be ordered on ONE stream.  The engine launches asynchronously on its own
+        stream by default, so every transform first binds it to torch's current stream on this device (a no-op
+        on the CPU emulator, whose calls are synchronous)."""
+        import torch
+
+        if torch.cuda.is_available() and self.eng.is_cuda():
+            self.eng.set_stream(torch.cuda.current_stream(self.eng.device).cuda_stream)
 
     # -- layouts (host helpers for tests / callers that hold the natural-order vector) ---------------
     def layout_a(self, x: np.ndarray) -> np.ndarray:
@@ -143,6 +154,7 @@ class DistNtt:
         import torch
 
         e = self.eng
+        self._bind_stream()
         if self.p2p:
             self.forward_into_exchange(data, coset)
             out = torch.empty_like(data)
@@ -158,6 +170,7 @@ class DistNtt:
     def forward_into_exchange(self, data, coset: Optional[int] = None) -> int:
         """p2p transport: layout A in `data` -> layout B left in this rank's exchange buffer (device pointer)."""
         e = self.eng
+        self._bind_stream()
         e.ntt_dist_stage_dev(data, self.log_n, self.rank, self.world, False, coset, peers=self._peers)
         self._sync_ranks()  # every rank's rows have landed
         e.ntt_dev(self._exch, self.s, batch=self.rows_local)
@@ -168,6 +181,7 @@ class DistNtt:
         import torch
 
         e = self.eng
+        self._bind_stream()
         if self.p2p:
             e.dev_copy(self._exch, data, self.local * 32)
             out = torch.empty_like(data)
@@ -183,6 +197,7 @@ class DistNtt:
     def inverse_from_exchange(self, out, coset: Optional[int] = None) -> None:
         """p2p transport: layout B in the exchange buffer -> layout A written to `out`."""
         e = self.eng
+        self._bind_stream()
         e.ntt_dev(self._exch, self.s, batch=self.rows_local, inverse=True)
         self._sync_ranks()  # peers' rows are final before anyone pulls them
         e.ntt_dist_stage_dev(out, self.log_n, self.rank, self.world, True, coset, peers=self._peers)
