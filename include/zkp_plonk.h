@@ -118,6 +118,20 @@ int zkp_plonk_quotient_dev(zkp_ctx* ctx, const zkp_plonk_quotient_args* args);
  * what makes prover.rs:404 `expect("No remainder 1")` hold. */
 int zkp_plonk_gate_check_dev(zkp_ctx* ctx, const void* const cols_dev[9], size_t n, int* ok);
 
+/* ---- Fiat-Shamir transcript pieces (plonk/src/challenge.rs:49-89), exposed so that known-answer tests can pin each
+ * third-party semantic the reference relies on against PUBLIC vectors (tests/test_transcript_kat.py): FIPS 180-4
+ * SHA-256, the PCG32 output function + rand_core 0.6 `seed_from_u64`, the ChaCha block function / word order / 64-bit
+ * counter of rand 0.8's StdRng (double_rounds = 6; 10 = ChaCha20 for RFC 8439 vectors), ark-bls12-381's uncompressed
+ * G1 encoding, and the whole `feed* -> generate_challenges` chain. ---- */
+void zkp_transcript_sha256(const uint8_t* data, size_t n, uint8_t out[32]);
+uint32_t zkp_transcript_pcg32_output(uint64_t state);
+void zkp_transcript_seed_from_u64(uint64_t seed, uint32_t key_out[8]);
+/* the first `count` 32-bit words of StdRng::from_seed(key) (key = eight little-endian words of the 32-byte seed) */
+void zkp_transcript_chacha_words(const uint32_t key[8], int double_rounds, size_t count, uint32_t* out);
+void zkp_transcript_g1_serialize(const uint64_t xy[12], uint8_t out[96]);
+/* ChallengeGenerator: feed(points[0..k)) then generate_challenges::<n>() -> n Fr (Montgomery); != 0 where it panics */
+int zkp_transcript_challenges(const uint64_t* points, size_t k, size_t n, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,8 +206,9 @@ def _rotl32(x, n):
     return ((x << n) | (x >> (32 - n))) & 0xFFFFFFFF
 
 
-def chacha12_block(key_words, counter: int):
-    """rand_chacha ChaCha12: 64-bit block counter in words 12-13, stream id 0 in words 14-15."""
+def chacha12_block(key_words, counter: int, double_rounds: int = 6):
+    """rand_chacha ChaCha12: 64-bit block counter in words 12-13, stream id 0 in words 14-15.
+    (double_rounds = 10 is ChaCha20: lets the KAT tests pin the block function on RFC 8439 vectors.)"""
     st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key_words) + \
          [counter & 0xFFFFFFFF, (counter >> 32) & 0xFFFFFFFF, 0, 0]
     x = list(st)
@@ -218,29 +219,51 @@ def chacha12_block(key_words, counter: int):
         x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = _rotl32(x[d] ^ x[a], 8)
         x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = _rotl32(x[b] ^ x[c], 7)
 
-    for _ in range(6):
+    for _ in range(double_rounds):
         qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
         qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
     return [(x[i] + st[i]) & 0xFFFFFFFF for i in range(16)]
 
 
-class StdRngFromU64:
-    """`StdRng::seed_from_u64` (rand_core 0.6 PCG32 seed expansion) + ChaCha12 word stream."""
+def pcg32_output(state: int) -> int:
+    """PCG XSH-RR 64/32 output function (rand_core's seed expansion uses it on the advanced state)."""
+    xorshifted = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+    rot = state >> 59
+    return ((xorshifted >> rot) | (xorshifted << ((32 - rot) & 31))) & 0xFFFFFFFF
 
-    def __init__(self, state: int):
-        words = []
-        for _ in range(8):
-            state = (state * 6364136223846793005 + 11634580027462260723) & (2**64 - 1)
-            xorshifted = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
-            rot = state >> 59
-            words.append(((xorshifted >> rot) | (xorshifted << ((32 - rot) & 31))) & 0xFFFFFFFF)
-        self.key = words
+
+def seed_from_u64(state: int) -> List[int]:
+    """rand_core 0.6 `SeedableRng::seed_from_u64`: eight PCG32 steps -> the eight little-endian key words."""
+    words = []
+    for _ in range(8):
+        state = (state * 6364136223846793005 + 11634580027462260723) & (2**64 - 1)
+        words.append(pcg32_output(state))
+    return words
+
+
+class StdRngFromU64:
+    """`StdRng::seed_from_u64` (rand_core 0.6 PCG32 seed expansion) + ChaCha12 word stream.
+    `StdRngFromU64.from_seed(bytes32)` is `StdRng::from_seed`."""
+
+    def __init__(self, state: Optional[int], key: Optional[List[int]] = None, double_rounds: int = 6):
+        self.key = seed_from_u64(state) if key is None else list(key)
+        self.double_rounds = double_rounds
         self.buf: List[int] = []
         self.ctr = 0
 
+    @classmethod
+    def from_seed(cls, seed: bytes, double_rounds: int = 6) -> "StdRngFromU64":
+        assert len(seed) == 32
+        return cls(None, key=[int.from_bytes(seed[4 * i:4 * i + 4], "little") for i in range(8)],
+                   double_rounds=double_rounds)
+
+    def fill_bytes(self, n: int) -> bytes:
+        assert n % 4 == 0
+        return b"".join(self.next_u32().to_bytes(4, "little") for _ in range(n // 4))
+
     def next_u32(self) -> int:
         if not self.buf:
-            self.buf = chacha12_block(self.key, self.ctr)
+            self.buf = chacha12_block(self.key, self.ctr, self.double_rounds)
             self.ctr += 1
         return self.buf.pop(0)
 

@@ -179,3 +179,26 @@ def test_msm_2p24_fixed_base_properties(zkp, gpu_engine, pyref):
     windowed, _ = gpu_engine.msm_dev(sr, bases, n)
     assert (fixed == windowed).all()
     gpu_engine.srs_upload_dev(bases, 1)  # drop the 18 GiB table
+
+
+def test_msm_2p24_random_scalars_vs_oracle(zkp, gpu_engine, coracle):
+    """The metric's own size, random scalars, FULL compare: 2^24-point MSM through the fixed-base table (the bench's
+    step, `KzgScheme::commit`'s path) and through the windowed path (ad-hoc bases) against the multi-threaded C oracle
+    (`orc_msm_pippenger`, ~15 s on 16 cores) -- kzg/src/scheme.rs:84-96 on the same buffers."""
+    import torch
+
+    F = zkp.fields
+    n = 1 << 24
+    bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
+    gpu_engine.generate_bases_dev(0x2426, n, bases)
+    s = F.random_fr_mont(0x2427, n)
+    want = coracle.msm_pippenger(s, _host(bases, 12))
+    sd = _dev(s)
+    windowed, inf = gpu_engine.msm_dev(sd, bases, n)
+    assert (windowed == want).all() and not inf
+    gpu_engine.srs_upload_dev(bases, n)
+    gpu_engine.srs_precompute()
+    fixed, inf = gpu_engine.msm_dev(sd, None, n)
+    assert gpu_engine.last_msm_shape()[0] >= 20
+    assert (fixed == want).all() and not inf
+    gpu_engine.srs_upload_dev(bases, 1)  # drop the table

@@ -136,9 +136,10 @@ def test_compile_errors(zkp, engine):
 
 
 def test_transcript_components():
-    """challenge.rs: SHA-256 chaining, PCG32 seed expansion, ChaCha12, Fr::rand -- fixed points of the
-    restatement that do not depend on the curve: RFC 8439-style ChaCha block structure (12 rounds) and
-    the aggregation_digest_test / safe_guard behaviours."""
+    """challenge.rs behaviours of the oracle's ChallengeGenerator: aggregation_digest_test / safe_guard
+    (challenge.rs:92-137), SHA-256 chaining of the uncompressed encodings.  The third-party pieces (SHA-256,
+    PCG32 seed expansion, ChaCha12 word / counter order, G1 bytes) are pinned against public known-answer vectors,
+    for this oracle AND for the product's host/transcript.hpp, in tests/test_transcript_kat.py."""
     g1 = ref.o.G1
     g2 = ref.o.g1_mul(g1, 2)
     a = ref.ChallengeGenerator(); a.feed(g1); a.feed(g2)

@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu", "poly.cu", "sort.cu"]
 HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
 HOST_DIR = os.path.join(PKG, "host")
-HOST_SOURCES = ["plonk.cpp", "kzg.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
+HOST_SOURCES = ["plonk.cpp", "kzg.cpp", "transcript_api.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
 HOST_HEADERS = ["mont_host.hpp", "transcript.hpp"]
 HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-Wall"]
 NVCC_FLAGS = [

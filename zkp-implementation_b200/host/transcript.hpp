@@ -92,13 +92,29 @@ class Sha256 {
 // ---- StdRng::seed_from_u64 + ChaCha12 ------------------------------------------------------------
 class StdRng {
  public:
-  explicit StdRng(uint64_t state) {
+  // PCG32 (XSH-RR) output function of rand_core's seed expansion; also the output function of the public pcg32
+  // generator, which is what tests/test_transcript_kat.py pins it against.
+  static uint32_t pcg32_output(uint64_t state) {
+    uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+    uint32_t rot = (uint32_t)(state >> 59);
+    return (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+  }
+  // rand_core 0.6 `SeedableRng::seed_from_u64`: eight PCG32 steps (advance, then output) -> 32-byte seed
+  static void seed_from_u64(uint64_t state, uint32_t key[8]) {
     for (int i = 0; i < 8; i++) {
       state = state * 6364136223846793005ull + 11634580027462260723ull;
-      uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
-      uint32_t rot = (uint32_t)(state >> 59);
-      key_[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+      key[i] = pcg32_output(state);
     }
+  }
+  explicit StdRng(uint64_t state) {
+    seed_from_u64(state, key_);
+    ctr_ = 0;
+    pos_ = 16;
+  }
+  // `StdRng::from_seed`: the 32 seed bytes are the eight little-endian key words.  double_rounds = 6 is ChaCha12
+  // (rand 0.8's StdRng); 10 gives ChaCha20 so the block function can be checked against RFC 8439 vectors.
+  explicit StdRng(const uint32_t key[8], int double_rounds = 6) : double_rounds_(double_rounds) {
+    for (int i = 0; i < 8; i++) key_[i] = key[i];
     ctr_ = 0;
     pos_ = 16;
   }
@@ -131,7 +147,7 @@ class StdRng {
 #define ZKP_QR(a, b, c, d) \
   x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12); \
   x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
-    for (int r = 0; r < 6; r++) {
+    for (int r = 0; r < double_rounds_; r++) {
       ZKP_QR(0, 4, 8, 12) ZKP_QR(1, 5, 9, 13) ZKP_QR(2, 6, 10, 14) ZKP_QR(3, 7, 11, 15)
       ZKP_QR(0, 5, 10, 15) ZKP_QR(1, 6, 11, 12) ZKP_QR(2, 7, 8, 13) ZKP_QR(3, 4, 9, 14)
     }
@@ -143,6 +159,7 @@ class StdRng {
   uint32_t out_[16];
   uint64_t ctr_;
   int pos_;
+  int double_rounds_ = 6;
 };
 
 // ---- G1 point as it crosses the C ABI: x || y Montgomery limbs, (0,0) = infinity ------------------

@@ -50,6 +50,13 @@ PLONK_ABI = {
     "zkp_plonk_numden_dev": (ctypes.c_int, [_vp, _vp]),
     "zkp_plonk_quotient_dev": (ctypes.c_int, [_vp, _vp]),
     "zkp_plonk_gate_check_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]),
+    # Fiat-Shamir transcript pieces (known-answer tests)
+    "zkp_transcript_sha256": (None, [_vp, ctypes.c_size_t, _vp]),
+    "zkp_transcript_pcg32_output": (ctypes.c_uint32, [ctypes.c_uint64]),
+    "zkp_transcript_seed_from_u64": (None, [ctypes.c_uint64, _vp]),
+    "zkp_transcript_chacha_words": (None, [_vp, ctypes.c_int, ctypes.c_size_t, _vp]),
+    "zkp_transcript_g1_serialize": (None, [_vp, _vp]),
+    "zkp_transcript_challenges": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_size_t, _vp]),
 }
 
 _PANICS = {
