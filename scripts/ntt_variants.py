@@ -3,13 +3,14 @@ The variant libraries are built HERE (nvcc cross-compiles) before the gpurun cal
 import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+K2 = ["-DNTT_KMAX=2", "-DNTT_TILE_LOG=10"]
 VARIANTS = {
-    "base": [],
-    "p2_t12_th512": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=512", "-DNTT_MIN_BLOCKS=1"],
-    "p2_t12_th256": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=256", "-DNTT_MIN_BLOCKS=1"],
-    "p2_t12_th1024": ["-DNTT_TILE_LOG=12", "-DNTT_RMAX=12", "-DNTT_WLOG=12", "-DNTT_THREADS_PER_CTA=1024", "-DNTT_MIN_BLOCKS=1"],
-    "r10_t11": ["-DNTT_RMAX=10"],
-    "r11_t11": ["-DNTT_RMAX=11"],
+    "k2_th128_b6_pre1": K2 + ["-DNTT_MIN_BLOCKS=6", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
+    "k2_th128_b6_pre0": K2 + ["-DNTT_MIN_BLOCKS=6", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=0"],
+    "k2_th256_b3_pre1": K2 + ["-DNTT_MIN_BLOCKS=3", "-DNTT_THREADS_PER_CTA=256", "-DNTT_TW_PRELOAD=1"],
+    "k2_th128_b5_pre1": K2 + ["-DNTT_MIN_BLOCKS=5", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
+    "k3_t11_th256_b2_pre1": ["-DNTT_TW_PRELOAD=1"],
+    "k3_t10_th128_b4_pre1": ["-DNTT_TILE_LOG=10", "-DNTT_MIN_BLOCKS=4", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
 }
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "zkp-implementation_b200", "build.py"))

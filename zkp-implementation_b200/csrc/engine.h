@@ -34,9 +34,11 @@ struct NttTables {
   uint32_t npass = 0;
   uint32_t digits[3] = {0, 0, 0};  // bits per pass, first pass = most significant input digit
   uint32_t lb = 0;                 // boundary tables: lo has 2^lb entries, hi has 2^(log_n - lb)
-  Fr* tw_lo = nullptr;             // omega_N^i            (inverse: omega_N^-i * N^-1)
+  // two-level inter-stage twiddles: only the distributed four-step stage uses them (the single-GPU passes read the
+  // per-level tables Ctx::tw_fwd / tw_inv and have no inter-pass product)
+  Fr* tw_lo = nullptr;             // omega_N^i            (inverse: omega_N^-i * (2^r)^-1)
   Fr* tw_hi = nullptr;             // omega_N^(i * 2^lb)   (inverse: omega_N^-(i * 2^lb))
-  Fr* scale = nullptr;             // N^-1 for a single-pass inverse transform, else null
+  Fr* scale = nullptr;             // N^-1 (inverse transforms), else null
 };
 
 struct CosetTables {
@@ -44,7 +46,8 @@ struct CosetTables {
   bool inverse = false;
   Fr offset;            // h (Montgomery)
   uint32_t lb = 0;
-  Fr* lo = nullptr;     // forward: h^i ; inverse: h^-i * N^-1 is NOT folded here (N^-1 stays in tw_lo/scale)
+  bool scaled = false;  // inverse tables of the single-GPU path carry N^-1 in `lo` (saves the separate scaling product)
+  Fr* lo = nullptr;     // forward: h^i ; inverse: h^-i (* N^-1 when `scaled`)
   Fr* hi = nullptr;     // forward: h^(i * 2^lb); inverse: h^-(i * 2^lb)
 };
 
@@ -72,8 +75,11 @@ struct Ctx {
   G1Affine* srs0_tab = nullptr;  // 32 x 256 byte-window table of srs[0] for commit_para (built on first use)
 
   // NTT state
-  Fr* w_fwd = nullptr;  // omega_{2^WLOG}^i, i < 2^(WLOG-1)
-  Fr* w_inv = nullptr;  // omega_{2^WLOG}^-i
+  // per-level butterfly twiddles, all orders in one array: T_k = [omega_{2^k}^i, i < 2^(k-1)] lives at
+  // [2^(k-1), 2^k), k = 1 .. tw_log (grown to the largest transform seen; 2^tw_log * 32 bytes per direction)
+  Fr* tw_fwd = nullptr;
+  Fr* tw_inv = nullptr;
+  uint32_t tw_log = 0;
   std::map<uint32_t, NttTables> ntt_tables;  // key = log_n * 2 + inverse
   std::vector<CosetTables> coset_tables;
   DevBuf ntt_scratch, ntt_io, ntt_io2;

@@ -9,15 +9,19 @@
 //   inverse  x[j] = h^-j N^-1 sum_k X[k] omega^(-jk)
 // Field arithmetic is exact, so any correct schedule is element-for-element identical.
 //
-// Schedule: N = N1 * N2 * N3 (<= 3 passes of <= 2^9 points).  Pass i runs, for every fixed value of
-// the other index digits, one N_i-point transform on a shared-memory tile that also carries 2^q
-// neighbouring columns (so every global access is a run of 2^q * 32 contiguous bytes), multiplies
-// by the inter-pass twiddle omega_{M_i}^(low * k_i) and writes the digit back in place.  The last
-// pass writes transposed, which puts the digit-reversed result in natural order without a separate
-// permutation sweep.  Pass 1 reads `data` and writes `scratch`, the last pass writes back to
-// `data`: 64 * N bytes of HBM traffic per pass, nothing else.
+// Schedule: log N = r1 + r2 + r3 (<= 3 passes of <= 10 levels).  The passes are consecutive groups of levels of ONE
+// decimation-in-frequency transform of size N: pass i runs its r_i levels on a shared-memory tile that holds 2^r_i
+// rows (stride 2^s apart) of 2^q neighbouring columns (so every global access is a run of 2^q * 32 contiguous
+// bytes).  A butterfly of the level of order 2^k multiplies by omega_{2^k}^(index mod 2^(k-1)), read from the
+// per-level table T_k -- the FULL twiddle, so there is no separate inter-pass product (the four-step formulation
+// spends one or two extra products per element and pass on omega_N^(col * digit)): a transform costs
+// (log N - 1) * N / 2 products and nothing else.  Only the first pass reads tables larger than L2 (T_logN ... :
+// N * 32 bytes in all, streamed once); later passes hit L1 / L2.  The last pass writes transposed, which puts the
+// digit-reversed result in natural order without a separate permutation sweep.  Pass 1 reads `data` and writes
+// `scratch`, the last pass writes back to `data`: 64 * N bytes of HBM traffic per pass.
 #include "engine.h"
 #include "memops.cuh"
+#include "poly.h"
 
 namespace zkp {
 
@@ -27,19 +31,28 @@ namespace zkp {
 #ifndef NTT_RMAX
 #define NTT_RMAX 10
 #endif
-static constexpr uint32_t WLOG = NTT_WLOG;  // sub-transform twiddle table: omega_{2^11}^i, i < 2^10
+static constexpr uint32_t WLOG = NTT_WLOG;  // the per-level twiddle tables always cover orders up to 2^11 (one tile)
 static constexpr uint32_t RMAX = NTT_RMAX;  // largest digit of a multi-pass schedule
+// Tile / CTA shape (measured on B200, profiles/r02_ntt_variants.txt): radix-4 register blocks (96 registers) with
+// 32 KB tiles and 128-thread CTAs keep 5 CTAs = 20 warps and five independent barrier domains per SM; the radix-8 /
+// 64 KB / 256-thread shape of round 1 (128 registers, 2 CTAs) was 15 % slower on the same schedule.
 #ifndef NTT_TILE_LOG
-#define NTT_TILE_LOG 11
+#define NTT_TILE_LOG 10
 #endif
 #ifndef NTT_THREADS_PER_CTA
-#define NTT_THREADS_PER_CTA 256
+#define NTT_THREADS_PER_CTA 128
 #endif
-static constexpr uint32_t TILE_LOG = NTT_TILE_LOG;   // elements per shared-memory tile (2^11 = 64 KB)
+static constexpr uint32_t TILE_LOG = NTT_TILE_LOG;   // elements per shared-memory tile (2^10 = 32 KB)
 static constexpr uint32_t SINGLE_MAX = NTT_TILE_LOG; // largest transform done in one tile
 static constexpr uint32_t NTT_THREADS = NTT_THREADS_PER_CTA;
 #ifndef NTT_MIN_BLOCKS
-#define NTT_MIN_BLOCKS 2
+#define NTT_MIN_BLOCKS 5
+#endif
+#ifndef NTT_KMAX
+#define NTT_KMAX 2  // levels per register block (2: radix-4, 3: radix-8)
+#endif
+#ifndef NTT_TW_PRELOAD
+#define NTT_TW_PRELOAD 1
 #endif
 
 struct NttPassArgs {
@@ -48,10 +61,11 @@ struct NttPassArgs {
   uint32_t log_n, r, q, s;
   uint32_t mode;      // 0: strided in-place digit, 1: last digit (transposing write)
   uint32_t log_n1, log_mid;
-  const Fr* w;        // sub-transform twiddles
-  const Fr* tw_lo;    // inter-pass twiddles (mode 0)
+  const Fr* w;        // per-level butterfly twiddles: T_k at [2^(k-1), 2^k)
+  uint32_t full_tw;   // 1: butterflies use the full order-2^(s + level) twiddle (single-GPU passes: no inter-pass product)
+  const Fr* tw_lo;    // two-level inter-stage twiddles (distributed stage only)
   const Fr* tw_hi;
-  uint32_t tw_lb, tw_shift, tw_two_level;
+  uint32_t tw_lb, tw_shift;
   const Fr* pre_lo;   // load-time scale by table[addr] (coset forward), or null
   const Fr* pre_hi;
   uint32_t pre_lb;
@@ -77,57 +91,119 @@ struct NttDistArgs {
 };
 
 // Shared-memory tile: two planes of 16-byte halves so that consecutive lanes touch consecutive
-// 16-byte words (conflict-free for unit-stride element access).
-__device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i) {
+// 16-byte words (conflict-free for unit-stride element access).  The slot of element i = (row << q) + c is
+// i ^ ((i >> sw) & 7), sw = max(q, 3): the low three column bits are XORed with the low row bits, so the eight
+// lanes of a quarter-warp hit eight different 16-byte bank groups both when they walk along a row (the butterfly
+// steps, the coalesced loads / stores of the strided passes) and when they walk down a column (the transposing
+// load of the last pass, which used to be an 8-way conflict).
+__device__ __forceinline__ uint32_t tile_slot(uint32_t i, uint32_t sw) { return i ^ ((i >> sw) & 7u); }
+__device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i, uint32_t sw) {
+  i = tile_slot(i, sw);
   uint4 a = lo[i], b = hi[i];
   Fr r;
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
   r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
-__device__ __forceinline__ void st_tile(uint4* lo, uint4* hi, uint32_t i, const Fr& r) {
+__device__ __forceinline__ void st_tile(uint4* lo, uint4* hi, uint32_t i, uint32_t sw, const Fr& r) {
+  i = tile_slot(i, sw);
   lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
   hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
 // K decimation-in-frequency levels (l0 .. l0+K-1 of an r-level transform along the tile rows) held
 // in registers: each work item owns the 2^K rows that differ in bits [lo_bit, lo_bit + K).
+// Twiddles: the level of local order 2^order_log belongs to the global level of order 2^(order_log + s_eff); element
+// (row j of the butterfly group, column col) reads T[(j << s_eff) + col] of that order (s_eff = 0, col = 0: plain
+// size-2^r transform along the rows).
+// The 2^K - 1 twiddles of one work item, level by level (level t contributes 2^(K-1-t) of them).
 template <int K>
-__device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, uint32_t r, uint32_t q, uint32_t l0,
-                                          const Fr* __restrict__ w, uint32_t tid, uint32_t nthreads) {
-  const uint32_t lo_bit = r - l0 - K;
-  const uint32_t items = 1u << (r - K + q);
-  const uint32_t qmask = (1u << q) - 1;
-  for (uint32_t it = tid; it < items; it += nthreads) {
-    const uint32_t c = it & qmask;
-    const uint32_t jr = it >> q;
-    const uint32_t dlow = jr & ((1u << lo_bit) - 1);
-    const uint32_t base_d = ((jr >> lo_bit) << (lo_bit + K)) | dlow;
-    Fr e[1 << K];
+struct TileTw {
+  Fr t[(1 << K) - 1];
+};
+
+struct TileGeom {
+  uint32_t r, q, sw, s_eff, colbase;
+  const Fr* __restrict__ w;
+};
+
+template <int K>
+__device__ __forceinline__ void tile_tw_load(TileTw<K>& tw, const TileGeom& g, uint32_t l0, uint32_t it) {
+  const uint32_t lo_bit = g.r - l0 - K;
+  const uint32_t c = it & ((1u << g.q) - 1);
+  const uint32_t dlow = (it >> g.q) & ((1u << lo_bit) - 1);
+  const uint32_t col = g.s_eff ? g.colbase + c : 0u;
+  int idx = 0;
 #pragma unroll
-    for (int m = 0; m < (1 << K); m++) e[m] = ld_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c);
+  for (int t = 0; t < K; t++) {
+    const int hm = 1 << (K - 1 - t);
+    const uint32_t order_log = lo_bit + K - t;  // butterflies of this level use omega_{2^(order_log + s_eff)}
+    const Fr* __restrict__ tk = g.w + ((size_t)1 << (order_log + g.s_eff - 1));
 #pragma unroll
-    for (int t = 0; t < K; t++) {
-      const int hm = 1 << (K - 1 - t);
-      const uint32_t order_log = lo_bit + K - t;  // butterflies of this level use omega_{2^order_log}
-      const uint32_t wshift = WLOG - order_log;
+    for (int mm = 0; mm < hm; mm++) {
+      const uint32_t j = dlow + ((uint32_t)mm << lo_bit);
+      // omega_2^0 = 1 on the very last level (slot 1 of the table array): never multiplied, see tile_block
+      tw.t[idx++] = ldg_fr(tk + (((size_t)j << g.s_eff) + col));
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void tile_block(uint4* lo, uint4* hi, const TileGeom& g, uint32_t l0, uint32_t it,
+                                           const TileTw<K>& tw) {
+  const uint32_t lo_bit = g.r - l0 - K;
+  const uint32_t q = g.q, sw = g.sw;
+  const uint32_t c = it & ((1u << q) - 1);
+  const uint32_t jr = it >> q;
+  const uint32_t dlow = jr & ((1u << lo_bit) - 1);
+  const uint32_t base_d = ((jr >> lo_bit) << (lo_bit + K)) | dlow;
+  Fr e[1 << K];
 #pragma unroll
-      for (int m = 0; m < (1 << K); m++) {
-        if (m & hm) continue;
-        Fr u = e[m], v = e[m + hm];
-        e[m] = fp_add(u, v);
-        Fr d = fp_sub(u, v);
-        if (order_log == 1) {
-          e[m + hm] = d;  // omega_2^0 = 1 on the last level
-        } else {
-          const uint32_t j = dlow + ((uint32_t)(m & (hm - 1)) << lo_bit);
-          e[m + hm] = fp_mul(d, ldg_fr(w + ((size_t)j << wshift)));
-        }
+  for (int m = 0; m < (1 << K); m++) e[m] = ld_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c, sw);
+  int off = 0;
+#pragma unroll
+  for (int t = 0; t < K; t++) {
+    const int hm = 1 << (K - 1 - t);
+    const uint32_t order_log = lo_bit + K - t;
+#pragma unroll
+    for (int m = 0; m < (1 << K); m++) {
+      if (m & hm) continue;
+      Fr u = e[m], v = e[m + hm];
+      e[m] = fp_add(u, v);
+      Fr d = fp_sub(u, v);
+      if (order_log + g.s_eff == 1) {
+        e[m + hm] = d;  // omega_2^0 = 1 on the very last level
+      } else {
+        e[m + hm] = fp_mul(d, tw.t[off + (m & (hm - 1))]);
       }
     }
-#pragma unroll
-    for (int m = 0; m < (1 << K); m++) st_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c, e[m]);
+    off += hm;
   }
+#pragma unroll
+  for (int m = 0; m < (1 << K); m++) st_tile(lo, hi, ((base_d + ((uint32_t)m << lo_bit)) << q) + c, sw, e[m]);
+}
+
+// One step = barrier + K levels.  The twiddles of the thread's first work item are requested BEFORE the barrier
+// (they do not depend on the tile), so their L2 / HBM latency overlaps the wait for the other warps.
+template <int K>
+__device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, const TileGeom& g, uint32_t l0, uint32_t tid,
+                                          uint32_t nthreads) {
+  const uint32_t items = 1u << (g.r - K + g.q);
+  TileTw<K> tw;
+#if NTT_TW_PRELOAD
+  if (tid < items) tile_tw_load<K>(tw, g, l0, tid);
+  __syncthreads();
+  for (uint32_t it = tid; it < items; it += nthreads) {
+    if (it != tid) tile_tw_load<K>(tw, g, l0, it);
+    tile_block<K>(lo, hi, g, l0, it, tw);
+  }
+#else
+  __syncthreads();
+  for (uint32_t it = tid; it < items; it += nthreads) {
+    tile_tw_load<K>(tw, g, l0, it);
+    tile_block<K>(lo, hi, g, l0, it, tw);
+  }
+#endif
 }
 
 template <bool DIST>
@@ -142,6 +218,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
   const Fr* in = a.in + (size_t)blockIdx.y * a.batch_stride;
   Fr* out = a.out + (size_t)blockIdx.y * a.batch_stride;
   const uint32_t qmask = (1u << q) - 1, rmask = (1u << r) - 1;
+  const uint32_t sw = q > 3 ? q : 3;
 
   // ---- tile geometry ----
   uint32_t base = 0, cb = 0, mid = 0, ab = 0;
@@ -184,7 +261,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
           v = fp_mul(v, ldg_fr(a.pre_lo + (gaddr & ((1u << a.pre_lb) - 1))));
           v = fp_mul(v, ldg_fr(a.pre_hi + (gaddr >> a.pre_lb)));
         }
-        st_tile(lo, hi, sidx, v);
+        st_tile(lo, hi, sidx, sw, v);
         continue;
       }
     } else {
@@ -198,30 +275,37 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
       v = fp_mul(v, ldg_fr(a.pre_lo + (addr & ((1u << a.pre_lb) - 1))));
       v = fp_mul(v, ldg_fr(a.pre_hi + (addr >> a.pre_lb)));
     }
-    st_tile(lo, hi, sidx, v);
+    st_tile(lo, hi, sidx, sw, v);
   }
-  __syncthreads();
 
   // ---- r DIF levels on the tile rows (result row d holds output digit bitrev_r(d)) ----
+  TileGeom g;
+  g.r = r; g.q = q; g.sw = sw;
+  g.s_eff = (!DIST && a.mode == 0 && a.full_tw) ? s : 0u;
+  g.colbase = cb << q;
+  g.w = a.w;
   uint32_t l0 = 0;
   while (r - l0 >= 3) {
-    tile_step<3>(lo, hi, r, q, l0, a.w, tid, nthreads);
-    __syncthreads();
+#if NTT_KMAX >= 3
+    tile_step<3>(lo, hi, g, l0, tid, nthreads);
     l0 += 3;
+#else  // radix-4 register blocks only (fewer live registers -> more resident warps, one more shared-memory round trip)
+    tile_step<2>(lo, hi, g, l0, tid, nthreads);
+    l0 += 2;
+#endif
   }
   if (r - l0 == 2) {
-    tile_step<2>(lo, hi, r, q, l0, a.w, tid, nthreads);
-    __syncthreads();
+    tile_step<2>(lo, hi, g, l0, tid, nthreads);
   } else if (r - l0 == 1) {
-    tile_step<1>(lo, hi, r, q, l0, a.w, tid, nthreads);
-    __syncthreads();
+    tile_step<1>(lo, hi, g, l0, tid, nthreads);
   }
+  __syncthreads();
 
   // ---- store: un-bit-reverse the digit, apply inter-pass twiddle / coset / N^-1 ----
   for (uint32_t idx = tid; idx < E; idx += nthreads) {
     const uint32_t c = idx & qmask, k = idx >> q;
     const uint32_t d = r ? (__brev(k) >> (32 - r)) : 0;
-    Fr v = ld_tile(lo, hi, (d << q) + c);
+    Fr v = ld_tile(lo, hi, (d << q) + c, sw);
     uint32_t addr;
     if (a.mode == 0) {
       const uint32_t col = (cb << q) + c;
@@ -245,9 +329,11 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
         }
         continue;
       }
-      const uint64_t e = ((uint64_t)col * k) << a.tw_shift;
-      v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
-      if (a.tw_two_level) v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
+      if (!a.full_tw) {  // four-step formulation (kept for A/B measurements): omega_M^(col * k), two-level table
+        const uint64_t e = ((uint64_t)col * k) << a.tw_shift;
+        v = fp_mul(v, ldg_fr(a.tw_hi + (size_t)(e >> a.tw_lb)));
+        v = fp_mul(v, ldg_fr(a.tw_lo + (size_t)(e & ((1u << a.tw_lb) - 1))));
+      }
       addr = base + (k << s) + c;
     } else {
       const uint32_t k1 = (ab << q) + c;
@@ -336,19 +422,51 @@ static int upload_powers(Ctx* ctx, Fr** dev, const Fr& base, const Fr& first, si
   return rt::sync(ctx->stream);
 }
 
+// Per-level twiddle tables T_1 .. T_log (both directions), built on the device; grown when a larger transform
+// shows up (the old arrays are released after the stream has drained).
+static int ensure_twiddles(Ctx* ctx, uint32_t log_n) {
+  const uint32_t need = log_n > WLOG ? log_n : WLOG;
+  if (ctx->tw_log >= need) return ZKP_OK;
+  Fr *f = nullptr, *b = nullptr;
+  const size_t count = (size_t)1 << need;
+  ZKP_TRY(rt::dev_malloc((void**)&f, count * sizeof(Fr)));
+  int st = rt::dev_malloc((void**)&b, count * sizeof(Fr));
+  const Fr one = Fr::one();
+  if (st == ZKP_OK) st = rt::h2d(f, &one, sizeof(Fr), ctx->stream);  // slot 0 is unused
+  if (st == ZKP_OK) st = rt::h2d(b, &one, sizeof(Fr), ctx->stream);
+  for (uint32_t k = 1; k <= need && st == ZKP_OK; k++) {
+    const Fr w = fr_omega(k);
+    const size_t half = (size_t)1 << (k - 1);
+    st = fr_powers_dev(ctx, f + half, w, one, half);
+    if (st == ZKP_OK) st = fr_powers_dev(ctx, b + half, fp_inv(w), one, half);
+  }
+  if (st == ZKP_OK) st = rt::sync(ctx->stream);
+  if (st != ZKP_OK) {
+    rt::dev_free(f);
+    rt::dev_free(b);
+    return st;
+  }
+  rt::dev_free(ctx->tw_fwd);
+  rt::dev_free(ctx->tw_inv);
+  ctx->tw_fwd = f;
+  ctx->tw_inv = b;
+  ctx->tw_log = need;
+  return ZKP_OK;
+}
+
 int ntt_init(Ctx* ctx) {
-  Fr w = fr_omega(WLOG);
-  ZKP_TRY(upload_powers(ctx, &ctx->w_fwd, w, Fr::one(), (size_t)1 << (WLOG - 1)));
-  ZKP_TRY(upload_powers(ctx, &ctx->w_inv, fp_inv(w), Fr::one(), (size_t)1 << (WLOG - 1)));
+  ZKP_TRY(ensure_twiddles(ctx, WLOG));
   ZKP_TRY(rt::allow_smem((const void*)ntt_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr)));
   ZKP_TRY(rt::allow_smem((const void*)ntt_dist_pass_kernel, ((size_t)1 << TILE_LOG) * sizeof(Fr)));
   ZKP_TRY(rt::prefer_smem_carveout((const void*)ntt_dist_pass_kernel));
-  return rt::prefer_smem_carveout((const void*)ntt_pass_kernel);  // several 64 KB tiles resident per SM
+  return rt::prefer_smem_carveout((const void*)ntt_pass_kernel);  // several tiles resident per SM
 }
 
 void ntt_destroy(Ctx* ctx) {
-  rt::dev_free(ctx->w_fwd);
-  rt::dev_free(ctx->w_inv);
+  rt::dev_free(ctx->tw_fwd);
+  rt::dev_free(ctx->tw_inv);
+  ctx->tw_fwd = ctx->tw_inv = nullptr;
+  ctx->tw_log = 0;
   for (auto& kv : ctx->ntt_tables) {
     rt::dev_free(kv.second.tw_lo);
     rt::dev_free(kv.second.tw_hi);
@@ -387,28 +505,30 @@ static int get_tables(Ctx* ctx, uint32_t log_n, bool inverse, NttTables** out) {
     const uint32_t b = log_n / t.npass, rem = log_n % t.npass;
     for (uint32_t i = 0; i < t.npass; i++) t.digits[i] = b + (i < rem ? 1 : 0);
   }
-  Fr n_inv = fp_inv(fr_from_u64((uint64_t)1 << log_n));
-  if (t.npass == 1) {
-    if (inverse) {
-      ZKP_TRY(upload_powers(ctx, &t.scale, Fr::one(), n_inv, 1));
-    }
-  } else {
+  if (inverse) {
+    const Fr n_inv = fp_inv(fr_from_u64((uint64_t)1 << log_n));
+    ZKP_TRY(upload_powers(ctx, &t.scale, Fr::one(), n_inv, 1));
+  }
+#ifdef NTT_FOUR_STEP_TWIDDLES  // A/B knob: the four-step formulation with its inter-pass products
+  if (t.npass > 1) {
     t.lb = t.digits[0];
     Fr w = fr_omega(log_n);
     if (inverse) w = fp_inv(w);
     Fr whi = w;
     for (uint32_t i = 0; i < t.lb; i++) whi = fp_sqr(whi);
-    ZKP_TRY(upload_powers(ctx, &t.tw_lo, w, inverse ? n_inv : Fr::one(), (size_t)1 << t.lb));
+    ZKP_TRY(upload_powers(ctx, &t.tw_lo, w, Fr::one(), (size_t)1 << t.lb));
     ZKP_TRY(upload_powers(ctx, &t.tw_hi, whi, Fr::one(), (size_t)1 << (log_n - t.lb)));
   }
+#endif
   auto ins = ctx->ntt_tables.emplace(key, t);
   *out = &ins.first->second;
   return ZKP_OK;
 }
 
-static int get_coset(Ctx* ctx, uint32_t log_n, bool inverse, const Fr& h, CosetTables** out) {
+// `scaled`: fold N^-1 into the low table (inverse transforms of the single-GPU path)
+static int get_coset(Ctx* ctx, uint32_t log_n, bool inverse, const Fr& h, bool scaled, CosetTables** out) {
   for (auto& c : ctx->coset_tables)
-    if (c.log_n == log_n && c.inverse == inverse && c.offset == h) {
+    if (c.log_n == log_n && c.inverse == inverse && c.scaled == scaled && c.offset == h) {
       *out = &c;
       return ZKP_OK;
     }
@@ -421,11 +541,13 @@ static int get_coset(Ctx* ctx, uint32_t log_n, bool inverse, const Fr& h, CosetT
   c.log_n = log_n;
   c.inverse = inverse;
   c.offset = h;
+  c.scaled = scaled;
   c.lb = log_n / 2;
   Fr g = inverse ? fp_inv(h) : h;
   Fr ghi = g;
   for (uint32_t i = 0; i < c.lb; i++) ghi = fp_sqr(ghi);
-  ZKP_TRY(upload_powers(ctx, &c.lo, g, Fr::one(), (size_t)1 << c.lb));
+  const Fr first = scaled ? fp_inv(fr_from_u64((uint64_t)1 << log_n)) : Fr::one();
+  ZKP_TRY(upload_powers(ctx, &c.lo, g, first, (size_t)1 << c.lb));
   ZKP_TRY(upload_powers(ctx, &c.hi, ghi, Fr::one(), (size_t)1 << (log_n - c.lb)));
   ctx->coset_tables.push_back(c);
   *out = &ctx->coset_tables.back();
@@ -440,10 +562,11 @@ int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, 
   if (log_n == 0) return ZKP_OK;  // size-1 domain: identity in both directions (h^0 = 1, 1^-1 = 1)
   NttTables* t = nullptr;
   ZKP_TRY(get_tables(ctx, log_n, inverse, &t));
+  ZKP_TRY(ensure_twiddles(ctx, log_n));
   CosetTables* cs = nullptr;
   if (coset_host) {
     const Fr one = Fr::one();
-    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, &cs));
+    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, inverse, &cs));
   }
   const size_t N = (size_t)1 << log_n;
   Fr* scratch = nullptr;
@@ -463,23 +586,25 @@ int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, 
     a.log_n = log_n;
     a.r = r;
     a.s = below;
-    a.w = inverse ? ctx->w_inv : ctx->w_fwd;
+    a.w = inverse ? ctx->tw_inv : ctx->tw_fwd;
     a.batch_stride = N;
+    a.full_tw = 1;
     if (!last) {
       a.mode = 0;
       a.q = (TILE_LOG - r < a.s) ? (TILE_LOG - r) : a.s;
+#ifdef NTT_FOUR_STEP_TWIDDLES
+      a.full_tw = 0;
       a.tw_lo = t->tw_lo;
       a.tw_hi = t->tw_hi;
       a.tw_lb = t->lb;
       a.tw_shift = log_n - (a.s + r);
-      a.tw_two_level = (a.tw_shift < t->lb) ? 1 : 0;
+#endif
     } else {
       a.mode = 1;
       if (t->npass == 1) {
         a.log_n1 = 0;
         a.log_mid = 0;
         a.q = 0;
-        a.scale = t->scale;
       } else {
         a.log_n1 = t->digits[0];
         a.log_mid = (t->npass == 3) ? t->digits[1] : 0;
@@ -487,7 +612,8 @@ int ntt_run_dev(Ctx* ctx, Fr* data, uint32_t log_n, size_t batch, bool inverse, 
       }
     }
     if (i == 0 && cs && !inverse) { a.pre_lo = cs->lo; a.pre_hi = cs->hi; a.pre_lb = cs->lb; }
-    if (last && cs && inverse) { a.post_lo = cs->lo; a.post_hi = cs->hi; a.post_lb = cs->lb; }
+    if (last && cs && inverse) { a.post_lo = cs->lo; a.post_hi = cs->hi; a.post_lb = cs->lb; }  // carries N^-1
+    if (last && inverse && !cs) a.scale = t->scale;
     const uint32_t E = 1u << (r + a.q);
     const uint32_t tiles = (uint32_t)(N >> (r + a.q));
     uint32_t threads = NTT_THREADS;
@@ -546,10 +672,11 @@ int ntt_dist_stage_dev(Ctx* ctx, Fr* data, uint32_t log_n, uint32_t rank, uint32
   if (r == 0 || log_n > 31 || world_log > 3 || rank >= (1u << world_log)) return ZKP_ERR_INVALID_ARG;
   NttTables* t = nullptr;
   ZKP_TRY(get_dist_tables(ctx, log_n, r, inverse, &t));
+  ZKP_TRY(ensure_twiddles(ctx, r));
   CosetTables* cs = nullptr;
   if (coset_host) {
     const Fr one = Fr::one();
-    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, &cs));
+    if (!(*coset_host == one)) ZKP_TRY(get_coset(ctx, log_n, inverse, *coset_host, false, &cs));
   }
   const uint32_t s_glob = log_n - r, s_loc = s_glob - world_log;
   NttPassArgs a;
@@ -561,12 +688,12 @@ int ntt_dist_stage_dev(Ctx* ctx, Fr* data, uint32_t log_n, uint32_t rank, uint32
   a.s = s_loc;
   a.q = (TILE_LOG - r < s_loc) ? (TILE_LOG - r) : s_loc;
   a.mode = 0;
-  a.w = inverse ? ctx->w_inv : ctx->w_fwd;
+  a.w = inverse ? ctx->tw_inv : ctx->tw_fwd;
+  a.full_tw = 0;  // the stage keeps the four-step twiddle omega_N^(col * k): its output crosses GPUs in that form
   a.tw_lo = t->tw_lo;
   a.tw_hi = t->tw_hi;
   a.tw_lb = t->lb;
   a.tw_shift = 0;
-  a.tw_two_level = 1;
   a.batch_stride = 0;
   if (cs && !inverse) { a.pre_lo = cs->lo; a.pre_hi = cs->hi; a.pre_lb = cs->lb; }
   if (cs && inverse) { a.post_lo = cs->lo; a.post_hi = cs->hi; a.post_lb = cs->lb; }
