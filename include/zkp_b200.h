@@ -54,12 +54,17 @@ int zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 int zkp_ctx_synchronize(zkp_ctx* ctx);
 /* Pippenger window width in bits (0 = pick from n). */
 int zkp_ctx_set_msm_window(zkp_ctx* ctx, uint32_t bits);
+/* Batched-affine tree rounds of the bucket accumulation (csrc/msm_affine.cu) before the XYZZ finish: -1 = pick from the
+ * mean bucket load (default), 0 = XYZZ only, R > 0 = exactly R rounds.  Any setting returns the same point. */
+int zkp_ctx_set_msm_affine(zkp_ctx* ctx, int rounds);
 /* Kernel launches issued by the last call of the given kind (0 = MSM, 1 = NTT); kind 2 / 3 return
- * the window width c / window count W the last MSM used. */
+ * the window width c / window count W the last MSM used, kind 4 its number of batched-affine rounds. */
 int zkp_ctx_last_launches(zkp_ctx* ctx, int kind);
 /* Per-phase device timing of the last MSM (CUDA events on the context's stream, recorded only when
- * profiling is on).  phase: 0 recode, 1 sort, 2 bucket boundaries + task list, 3 accumulate,
- * 4 bucket/window reduction.  Returns milliseconds, or a negative value if nothing was recorded. */
+ * profiling is on).  phase: 0 recode, 1 sort, 2 bucket boundaries, 3 accumulate (batched-affine rounds + task list +
+ * XYZZ finish), 4 bucket/window reduction.  Returns milliseconds, or a negative value if nothing was recorded.
+ * phase 100: the first batched-affine round's addition kernel alone (the longest launch of a large MSM);
+ * phase 200 + r: points entering round 1 (r = 0) / leaving round r (counts, not times). */
 int zkp_ctx_set_profiling(zkp_ctx* ctx, int on);
 double zkp_ctx_last_phase_ms(zkp_ctx* ctx, int phase);
 const char* zkp_strerror(int status);
@@ -185,6 +190,9 @@ int zkp_scan_exclusive_u32_dev(zkp_ctx* ctx, const void* in_dev, void* out_dev, 
 /* ---- synthetic workloads (bench configs 2/5): n distinct pseudo-random G1 points generated on
  *      the device from a seed (a0 + i*delta) * G, affine, written to bases_dev (n x 96 B). ----- */
 int zkp_g1_generate_bases_dev(zkp_ctx* ctx, uint64_t seed, size_t n, void* bases_dev);
+/* points [first, first + n) of the same progression: a rank's shard of a point set that does not depend on the number
+ * of ranks (config 5: the sharded 2^26 MSM computes the same point at 1, 2, 4 and 8 GPUs). */
+int zkp_g1_generate_bases_range_dev(zkp_ctx* ctx, uint64_t seed, size_t first, size_t n, void* bases_dev);
 
 /* ---- integer-pipe microbenchmark: the MSM roofline denominator.
  *      Runs independent 32x32->64 multiply-add chains on every SM and returns multiply-adds/s. */

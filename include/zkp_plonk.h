@@ -89,6 +89,13 @@ int zkp_plonk_prove_sharded(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const ui
 int zkp_plonk_prove_products(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
                              double* timings_ms);
 
+/* zkp_plonk_prove_products with `compute_acc` exactly as prover.rs:302-377 writes it: nine Horner evaluations of
+ * degree-n polynomials and one field division per row (O(n^2)).  Same bytes again; it exists so that the reference's
+ * own algorithm can be timed step for step (bench.py's host-CPU PLONK baseline links this file against a CPU backend
+ * of the C ABI, oracle/cpu_backend.cpp) and as a third cross-check at small n. */
+int zkp_plonk_prove_reference(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                              double* timings_ms);
+
 /* ---- the two pointwise kernels of the device-resident prover (csrc/poly.cu) -------------------------- */
 /* prover.rs:314-369: num[i], den[i] of the grand-product factor at row i, from the wire / sigma VALUES on the
  * domain and roots[i] = omega^i. */

@@ -162,3 +162,55 @@ def test_multi_msm_one_pipeline(zkp, engine, coracle):
         got = engine.msm_multi_dev([dv[0].ptr, dv[0].ptr], [n, 0])
         assert (got[0][0] == want[0]).all() and got[1][1]
     engine.srs_upload(b[:1])
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5, 12])
+def test_batched_affine_rounds(zkp, engine, coracle, pyref, rounds):
+    """csrc/msm_affine.cu: R batched-affine tree rounds before the XYZZ finish return the same point as R = 0 and the
+    oracle -- random scalars at two window widths (long and short runs, odd run lengths, empty buckets), the fixed-base
+    table, and every special case of the affine adder: infinity bases, one point repeated (P + P in every round until
+    the run is gone), P and -P (cancellation to O inside a run), all-equal scalars (one bucket holds everything; more
+    rounds than the run is deep)."""
+    F = zkp.fields
+    n = 500
+    b = coracle.srs(F.fr_to_mont_array([0xAFF1]), n)
+    b[11] = 0
+    b[12] = 0
+    s = F.random_fr_mont(91, n)
+    s[7] = 0
+    engine.set_msm_affine(rounds)
+    try:
+        for window in (4, 9):
+            engine.set_msm_window(window)
+            out, inf = engine.msm(s, b)
+            assert engine.last_affine_rounds() == rounds
+            assert (out == coracle.msm_pippenger(s, b)).all() and not inf, window
+        engine.set_msm_window(0)
+        # one bucket per window holds every point
+        for val in (1, 5, pyref.R - 1):
+            sv = F.fr_to_mont_array([val] * n)
+            assert (engine.msm(sv, b)[0] == coracle.msm_pippenger(sv, b)).all(), val
+        # the same point n times: doublings all the way down
+        same = np.repeat(b[5:6], 333, axis=0)
+        out, inf = engine.msm(F.fr_to_mont_array([9] * 333), same)
+        assert affine_of(zkp, out, inf) == pyref.g1_mul(F.g1_from_array(b[5])[0], 9 * 333)
+        # P, -P, P, -P ...: every pair cancels; then with one extra P
+        p = F.g1_from_array(b[9])[0]
+        pair = F.g1_to_array([p, pyref.g1_neg(p)] * 10)
+        assert engine.msm(F.fr_to_mont_array([12345] * 20), pair)[1]
+        odd = F.g1_to_array([p, pyref.g1_neg(p)] * 10 + [p])
+        out, inf = engine.msm(F.fr_to_mont_array([12345] * 21), odd)
+        assert affine_of(zkp, out, inf) == pyref.g1_mul(p, 12345)
+        # fixed-base table + a batch of commitments as bucket sets
+        engine.srs_upload(b)
+        engine.srs_precompute(6)
+        assert (engine.msm(s)[0] == coracle.msm_pippenger(s, b)).all()
+        vecs = [F.random_fr_mont(92, n), F.random_fr_mont(93, 321)]
+        dv = [engine.vec(v) for v in vecs]
+        got = engine.msm_multi_dev([d.ptr for d in dv], [v.shape[0] for v in vecs])
+        for j, (o, i) in enumerate(got):
+            assert (o == coracle.msm_pippenger(vecs[j], b[:vecs[j].shape[0]])).all() and not i, j
+    finally:
+        engine.set_msm_affine(-1)
+        engine.set_msm_window(0)
+        engine.srs_upload(b[:1])

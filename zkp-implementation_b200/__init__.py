@@ -31,6 +31,7 @@ ABI = {
     "zkp_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "zkp_ctx_set_msm_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
+    "zkp_ctx_set_msm_affine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "zkp_ctx_last_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "zkp_ctx_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "zkp_ctx_last_phase_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
@@ -92,6 +93,8 @@ ABI = {
                                           ctypes.c_int]),
     "zkp_scan_exclusive_u32_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zkp_g1_generate_bases_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p]),
+    "zkp_g1_generate_bases_range_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t,
+                                                       ctypes.c_void_p]),
     "zkp_bench_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
 }
@@ -174,6 +177,13 @@ class Engine:
     def set_msm_window(self, bits: int) -> None:
         self._check(self.lib.zkp_ctx_set_msm_window(self._h, bits))
 
+    def set_msm_affine(self, rounds: int) -> None:
+        """Batched-affine tree rounds before the XYZZ finish (-1 = automatic, 0 = off)."""
+        self._check(self.lib.zkp_ctx_set_msm_affine(self._h, rounds))
+
+    def last_affine_rounds(self) -> int:
+        return int(self.lib.zkp_ctx_last_launches(self._h, 4))
+
     def last_launches(self, kind: str) -> int:
         return int(self.lib.zkp_ctx_last_launches(self._h, 0 if kind == "msm" else 1))
 
@@ -188,6 +198,13 @@ class Engine:
 
     def last_phase_ms(self) -> dict:
         return {name: float(self.lib.zkp_ctx_last_phase_ms(self._h, i)) for i, name in enumerate(self.PHASES)}
+
+    def last_affine_profile(self) -> dict:
+        """First-round addition kernel time and the number of points entering / leaving each batched-affine round of
+        the last MSM (profiling on)."""
+        r = self.last_affine_rounds()
+        pts = [int(self.lib.zkp_ctx_last_phase_ms(self._h, 200 + i)) for i in range(min(r, 7) + 1)] if r else []
+        return {"rounds": r, "add_kernel_round1_ms": float(self.lib.zkp_ctx_last_phase_ms(self._h, 100)), "points": pts}
 
     # -- SRS --------------------------------------------------------------------------------------
     def srs_upload(self, xy: np.ndarray, infinity: Optional[np.ndarray] = None) -> None:
@@ -398,8 +415,8 @@ class Engine:
         self._check(self.lib.zkp_scan_exclusive_u32_dev(self._h, _ptr(in_dev), _ptr(out_dev), n))
 
     # -- synthetic workloads / microbenchmarks ----------------------------------------------------
-    def generate_bases_dev(self, seed: int, n: int, bases_dev) -> None:
-        self._check(self.lib.zkp_g1_generate_bases_dev(self._h, seed & (2**64 - 1), n, _ptr(bases_dev)))
+    def generate_bases_dev(self, seed: int, n: int, bases_dev, first: int = 0) -> None:
+        self._check(self.lib.zkp_g1_generate_bases_range_dev(self._h, seed & (2**64 - 1), first, n, _ptr(bases_dev)))
 
     def imad_peak(self) -> Tuple[float, float]:
         w, l = ctypes.c_double(0), ctypes.c_double(0)

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "gen.cu", "poly.cu", "sort.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_affine.cu", "gen.cu", "poly.cu", "sort.cu"]
 HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
 HOST_DIR = os.path.join(PKG, "host")
 HOST_SOURCES = ["plonk.cpp", "kzg.cpp", "transcript_api.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
@@ -59,7 +59,10 @@ def _host_objs(bdir: str) -> list[str]:
     return objs
 
 
-def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_name: str = "libzkp_b200.so") -> str:
+def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_name: str = "libzkp_b200.so",
+               only: list[str] | None = None) -> str:
+    """`only`: build-variant shortcut -- recompile just these sources with `extra_flags` and link them with the
+    objects of the default build (which must exist)."""
     out = os.path.join(PKG, out_name)
     if not force and _newer(out, _deps() + [os.path.abspath(__file__)]):
         return out
@@ -68,14 +71,21 @@ def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_na
     os.makedirs(bdir, exist_ok=True)
     flags = NVCC_FLAGS + (extra_flags or [])
 
+    base_dir = os.path.join(PKG, "build", "libzkp_b200")
+
     def one(src: str) -> str:
+        if only is not None and src not in only:
+            return os.path.join(base_dir, src.replace(".cu", ".o"))
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
         _run([nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj], log=obj + ".log")
         return obj
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    objs += _host_objs(bdir)
+    if only is not None:
+        objs += [os.path.join(base_dir, s.replace(".cpp", ".host.o")) for s in HOST_SOURCES]
+    else:
+        objs += _host_objs(bdir)
     # --cudart shared: the CUDA runtime is resolved from the image (or shared with torch when torch loaded it first)
     # instead of being embedded in the product library
     _run([nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",

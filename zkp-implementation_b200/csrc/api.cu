@@ -17,6 +17,7 @@ struct zkp_ctx {
 
 namespace zkp {
 int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out);
+int gen_bases_range_dev(Ctx* ctx, uint64_t seed, size_t first, size_t n, G1Affine* out);
 int gen_srs_dev(Ctx* ctx, const Fr& secret, size_t start, size_t n, G1Affine* out);
 int bench_imad(Ctx* ctx, double* wide, double* lo);
 }  // namespace zkp
@@ -133,6 +134,13 @@ int zkp_ctx_set_msm_window(zkp_ctx* h, uint32_t bits) {
   return ZKP_OK;
 }
 
+int zkp_ctx_set_msm_affine(zkp_ctx* h, int rounds) {
+  if (!h || rounds < -1 || rounds > 30) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);
+  h->c.msm_affine_rounds = rounds;
+  return ZKP_OK;
+}
+
 int zkp_ctx_set_profiling(zkp_ctx* h, int on) {
   if (!h) return ZKP_ERR_INVALID_ARG;
   h->c.profiling = on != 0;
@@ -140,6 +148,8 @@ int zkp_ctx_set_profiling(zkp_ctx* h, int on) {
 }
 
 double zkp_ctx_last_phase_ms(zkp_ctx* h, int phase) {
+  if (h && phase == 100) return (double)h->c.aff_add1_ms;  // first-round batched-affine addition kernel
+  if (h && phase >= 200 && phase < 200 + Ctx::AFF_STATS) return (double)h->c.aff_stats[phase - 200];  // points per round
   if (!h || phase < 0 || phase >= Ctx::NPHASE) return -1.0;
   return (double)h->c.phase_ms[phase];
 }
@@ -147,6 +157,7 @@ double zkp_ctx_last_phase_ms(zkp_ctx* h, int phase) {
 int zkp_ctx_last_launches(zkp_ctx* h, int kind) {
   if (h && kind == 2) return (int)h->c.last_window_bits;
   if (h && kind == 3) return (int)h->c.last_windows;
+  if (h && kind == 4) return (int)h->c.last_affine_rounds;
   if (!h) return 0;
   return kind == 0 ? (int)h->c.msm_launches : (int)h->c.ntt_launches;
 }
@@ -688,6 +699,13 @@ int zkp_g1_generate_bases_dev(zkp_ctx* h, uint64_t seed, size_t n, void* bases_d
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   return gen_bases_dev(&h->c, seed, n, (G1Affine*)bases_dev);
+}
+
+int zkp_g1_generate_bases_range_dev(zkp_ctx* h, uint64_t seed, size_t first, size_t n, void* bases_dev) {
+  if (!h || (n && !bases_dev)) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(h->c.mu);
+  ZKP_TRY(rt::set_device(h->c.device));
+  return gen_bases_range_dev(&h->c, seed, first, n, (G1Affine*)bases_dev);
 }
 
 int zkp_bench_imad_peak(zkp_ctx* h, double* wide, double* lo) {

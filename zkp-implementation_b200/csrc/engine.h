@@ -57,6 +57,8 @@ struct MsmScratch {
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
   DevBuf bucket_start, bucket_end, task_meta, partials, seg_out, win_out;
   DevBuf misc;
+  // batched-affine tree rounds (msm_affine.cu): ping-pong point buffers, denominator prefixes, inversion tree, run offsets
+  DevBuf aff_a, aff_b, aff_pre, aff_inv, aff_off;
 };
 
 struct Ctx {
@@ -95,6 +97,8 @@ struct Ctx {
   // MSM state
   MsmScratch msm;
   uint32_t msm_window_bits = 0;  // 0 = choose from n
+  int msm_affine_rounds = -1;    // batched-affine tree rounds before the XYZZ finish; -1 = choose from the mean bucket load
+  uint32_t last_affine_rounds = 0;
   uint32_t msm_launches = 0;     // kernels launched by the last MSM (bench.py's gpu_launches)
   uint32_t ntt_launches = 0;
 
@@ -103,6 +107,13 @@ struct Ctx {
   bool profiling = false;
   void* phase_ev[NPHASE + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float phase_ms[NPHASE] = {-1, -1, -1, -1, -1};
+  // profiling of the batched-affine rounds: events around the first round's addition kernel (the longest launch of an
+  // MSM) and the number of points entering / leaving every round (device counters read back after the final sync)
+  void* aff_ev[2] = {nullptr, nullptr};
+  float aff_add1_ms = -1;
+  static constexpr int AFF_STATS = 8;
+  uint32_t* aff_stats_dev = nullptr;      // [AFF_STATS]: [0] points before round 1, [r] points after round r
+  uint32_t aff_stats[AFF_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t last_window_bits = 0, last_windows = 0;
 };
 
@@ -128,6 +139,12 @@ int msm_run_dev(Ctx* ctx, const Fr* scalars_dev, const G1Affine* bases_dev, size
 int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_list, uint32_t count, const G1Affine* bases,
                       G1Xyzz* out_host, uint32_t fixed_c, size_t table_stride);
 int msm_precompute_dev(Ctx* ctx, uint32_t window_bits);
+// batched-affine tree rounds over the bucket-sorted point list (msm_affine.cu)
+uint32_t msm_affine_choose_rounds(size_t total, size_t total_buckets);
+size_t msm_affine_bound(size_t total, size_t nb, uint32_t rounds);
+int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, const G1Affine* bases, const uint32_t* bstart,
+                          const uint32_t* bend, uint32_t nb, size_t total, const G1Affine** pts, const uint32_t** off,
+                          size_t* bound);
 
 // ---- sort / scan (sort.cu) ----
 // Stable LSD radix sort of n (key, value) pairs by the low key_bits of the key; the result is in (*kres, *vres), one

@@ -118,9 +118,14 @@ int normalise_dev(Ctx* ctx, const G1Xyzz* tmp, size_t n, G1Affine* out) {
   return rt::check_last();
 }
 
-int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
+int gen_bases_range_dev(Ctx* ctx, uint64_t seed, size_t first, size_t n, G1Affine* out);
+int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) { return gen_bases_range_dev(ctx, seed, 0, n, out); }
+
+// points [first, first + n) of the progression: a shard of a larger synthetic point set (multi-GPU runs generate
+// the SAME global set whatever the number of ranks)
+int gen_bases_range_dev(Ctx* ctx, uint64_t seed, size_t first, size_t n, G1Affine* out) {
   if (n == 0) return ZKP_OK;
-  if (n >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
+  if (n >= ((size_t)1 << 32) || first >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
   uint64_t s = seed;
   uint32_t a0[8], dl[8];
   for (int i = 0; i < 4; i++) {
@@ -132,8 +137,12 @@ int gen_bases_dev(Ctx* ctx, uint64_t seed, size_t n, G1Affine* out) {
   dl[7] &= 0x3fffffffu;
   dl[0] |= 1;
   const G1Xyzz g = G1Xyzz::from_affine(g1_generator());
-  const G1Xyzz start = xyzz_mul_limbs(g, a0, 8);
+  G1Xyzz start = xyzz_mul_limbs(g, a0, 8);
   const G1Affine step = xyzz_to_affine(xyzz_mul_limbs(g, dl, 8));
+  if (first) {
+    const G1Xyzz skip = xyzz_mul_u32(G1Xyzz::from_affine(step), (uint32_t)first);
+    xyzz_add(start, skip);
+  }
   DevBuf tmp;
   ZKP_TRY(tmp.reserve(n * sizeof(G1Xyzz) + sizeof(G1Xyzz) + sizeof(G1Affine)));
   // chain parameters live in device memory (large by-value kernel parameters are avoided)

@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __r
 }
 
 // ---- 5. accumulate -------------------------------------------------------------------------------
+// DIRECT = false: the run is a slice of the sorted (point index | sign) list and the points are gathered from `bases`;
+// DIRECT = true: the run is a slice of `bases` itself (the output of the batched-affine tree rounds, msm_affine.cu).
+template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks,
                                                                      const uint32_t* __restrict__ order, uint32_t ntasks,
                                                                      const uint32_t* __restrict__ svals,
@@ -198,16 +201,21 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTa
   if (slot >= ntasks) return;
   const uint32_t t = order[slot];  // longest runs first; partials stay in bucket order
   const MsmTask tk = tasks[t];
-  const uint32_t* v = svals + tk.start;
+  const uint32_t* v = DIRECT ? nullptr : svals + tk.start;
+  const G1Affine* run = bases + tk.start;
   G1Xyzz acc = G1Xyzz::infinity();
-  uint32_t pv = v[0];
-  G1Affine nxt = ld_affine(bases + (pv & ~SIGN_BIT));
+  uint32_t pv = DIRECT ? 0u : v[0];
+  G1Affine nxt = DIRECT ? ld_affine(run) : ld_affine(bases + (pv & ~SIGN_BIT));
   for (uint32_t i = 0; i < tk.len; i++) {
     G1Affine cur = nxt;
     const uint32_t cv = pv;
     if (i + 1 < tk.len) {
-      pv = v[i + 1];
-      nxt = ld_affine(bases + (pv & ~SIGN_BIT));
+      if (DIRECT) {
+        nxt = ld_affine(run + i + 1);
+      } else {
+        pv = v[i + 1];
+        nxt = ld_affine(bases + (pv & ~SIGN_BIT));
+      }
     }
     if (cv & SIGN_BIT) cur = g1_neg(cur);
     xyzz_madd(acc, cur);
@@ -480,6 +488,14 @@ static void phase_collect(Ctx* ctx) {
       ms = -1;
     ctx->phase_ms[i] = ms;
   }
+  ctx->aff_add1_ms = -1;
+  memset(ctx->aff_stats, 0, sizeof(ctx->aff_stats));
+  if (ctx->last_affine_rounds && ctx->aff_ev[0] && ctx->aff_ev[1]) {
+    float ms = -1;
+    if (cudaEventElapsedTime(&ms, (cudaEvent_t)ctx->aff_ev[0], (cudaEvent_t)ctx->aff_ev[1]) == cudaSuccess) ctx->aff_add1_ms = ms;
+    if (ctx->aff_stats_dev)  // the stream has been synchronised by the caller
+      cudaMemcpy(ctx->aff_stats, ctx->aff_stats_dev, sizeof(ctx->aff_stats), cudaMemcpyDeviceToHost);
+  }
 #else
   (void)ctx;
 #endif
@@ -516,12 +532,6 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   const size_t total = n_sum * nwin;
   if (total >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
   if (fixed && (size_t)nwin * table_stride >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
-  // bound the longest run one thread owns: 4x the mean bucket load, but never so long that fewer than ~128 K
-  // tasks exist (few, heavily loaded buckets), and at least 32
-  uint32_t smax = (uint32_t)((4 * total) / total_buckets);
-  if (smax > total / 131072) smax = (uint32_t)(total / 131072);
-  if (smax < 32) smax = 32;
-  const size_t max_tasks = (size_t)total_buckets + total / smax + 1;
   // reduction levels: X^l has nbuckets >> l entries per set, l = 0 .. c - 1 (the last one is G)
   const uint32_t levels = c - 1;
   if (levels + 1 > 32 || levels > MAX_RED_LEVELS) return ZKP_ERR_INVALID_ARG;
@@ -537,8 +547,6 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.bucket_start.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.bucket_end.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
-  ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
-  ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
   // stage-1 blocks per (level, set): enough for ~2 waves over all sets at the widest level, never more than one
   // block per min_chunk entries
   const uint32_t min_chunk = ((size_t)nbuckets * nsets <= ((size_t)1 << 17)) ? SUM_CHUNK_SMALL : SUM_CHUNK_LARGE;
@@ -560,12 +568,6 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   uint32_t* task_off = ntask + (total_buckets + 1);
   uint32_t* nfold = task_off + (total_buckets + 1);  // ntask after heavy buckets were folded to one partial
   uint32_t* heavy = nfold + (total_buckets + 1);
-  MsmTask* tasks = m.task_meta.as<MsmTask>();
-  uint32_t* task_len = reinterpret_cast<uint32_t*>(tasks + max_tasks);
-  uint32_t* task_id = task_len + max_tasks;
-  uint32_t* task_len_sorted = task_id + max_tasks;
-  uint32_t* task_order = task_len_sorted + max_tasks;
-  G1Xyzz* partials = m.partials.as<G1Xyzz>();
   G1Xyzz* lvl_buf = m.seg_out.as<G1Xyzz>();
   G1Xyzz* win_out = m.win_out.as<G1Xyzz>();  // [nsets]
   cudaStream_t st = ctx->stream;
@@ -602,27 +604,70 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
                       bstart, bend);
     ctx->msm_launches++;
   }
+  phase_mark(ctx, 3);
+  // 3b. batched-affine tree rounds (msm_affine.cu): every run of L points becomes ~L / 2^R points at ~6 field products
+  // per addition instead of 10; what is left is accumulated in XYZZ below
+  uint32_t rounds = ctx->msm_affine_rounds >= 0 ? (uint32_t)ctx->msm_affine_rounds
+                                                : msm_affine_choose_rounds(total, total_buckets);
+  const uint32_t* run_start = bstart;
+  const uint32_t* run_end = bend;
+  const G1Affine* run_pts = nullptr;
+  size_t total_fin = total;
+  if (rounds) {
+    const uint32_t* off = nullptr;
+    const int as = msm_affine_rounds_dev(ctx, rounds, svals, bases, bstart, bend, total_buckets, total, &run_pts, &off, &total_fin);
+    if (as == ZKP_ERR_OOM) {  // the round buffers do not fit next to the table: plain XYZZ accumulation
+      rounds = 0;
+      run_pts = nullptr;
+      total_fin = total;
+#ifndef ZKP_EMU
+      cudaGetLastError();
+#endif
+    } else {
+      ZKP_TRY(as);
+      run_start = off;
+      run_end = off + 1;
+    }
+  }
+  ctx->last_affine_rounds = rounds;
+  // bound the longest run one thread owns: 4x the mean bucket load, but never so long that fewer than ~128 K
+  // tasks exist (few, heavily loaded buckets), and at least 32
+  uint32_t smax = (uint32_t)((4 * total_fin) / total_buckets);
+  if (smax > total_fin / 131072) smax = (uint32_t)(total_fin / 131072);
+  if (smax < 32) smax = 32;
+  const size_t max_tasks = (size_t)total_buckets + total_fin / smax + 1;
+  ZKP_TRY(m.task_meta.reserve(max_tasks * (sizeof(MsmTask) + 4 * sizeof(uint32_t))));
+  ZKP_TRY(m.partials.reserve(max_tasks * sizeof(G1Xyzz)));
+  MsmTask* tasks = m.task_meta.as<MsmTask>();
+  uint32_t* task_len = reinterpret_cast<uint32_t*>(tasks + max_tasks);
+  uint32_t* task_id = task_len + max_tasks;
+  uint32_t* task_len_sorted = task_id + max_tasks;
+  uint32_t* task_order = task_len_sorted + max_tasks;
+  G1Xyzz* partials = m.partials.as<G1Xyzz>();
   // 4. tasks
   ZKP_TRY(rt::dev_memset(ntask + total_buckets, 0, 4, st));
   ZKP_TRY(rt::dev_memset(heavy, 0, 4, st));
-  ZKP_LAUNCH_NOSYNC(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, total_buckets, smax,
-             ntask, heavy);
+  ZKP_LAUNCH_NOSYNC(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, run_start, run_end,
+             total_buckets, smax, ntask, heavy);
   ZKP_TRY(exclusive_scan_u32(ctx, ntask, task_off, total_buckets + 1));
-  ZKP_LAUNCH_NOSYNC(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, bstart, bend, task_off,
+  ZKP_LAUNCH_NOSYNC(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, run_start, run_end, task_off,
              total_buckets, smax, tasks, task_len, task_id);
   ctx->msm_launches += 2;
   uint32_t ntasks = 0;
   ZKP_TRY(rt::d2h(&ntasks, task_off + total_buckets, 4, st));
   ZKP_TRY(rt::sync(st));
-  // 5. accumulate
-  phase_mark(ctx, 3);
+  // 5. accumulate (XYZZ finish)
   if (ntasks) {
     uint32_t len_bits = 1;
     while ((1u << len_bits) <= smax) len_bits++;
     uint32_t *len_sorted = nullptr, *order = nullptr;
     ZKP_TRY(sort_pairs(ctx, task_len, task_id, task_len_sorted, task_order, ntasks, len_bits, true, &len_sorted, &order));
-    ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st, tasks,
-               (const uint32_t*)order, ntasks, (const uint32_t*)svals, bases, partials);
+    if (run_pts)
+      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<true>, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
+                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks, (const uint32_t*)nullptr, run_pts, partials);
+    else
+      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<false>, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
+                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks, (const uint32_t*)svals, bases, partials);
     ctx->msm_launches += 1;
   }
   // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
@@ -725,12 +770,17 @@ void msm_destroy(Ctx* ctx) {
 #ifndef ZKP_EMU
   for (int i = 0; i <= Ctx::NPHASE; i++)
     if (ctx->phase_ev[i]) { cudaEventDestroy((cudaEvent_t)ctx->phase_ev[i]); ctx->phase_ev[i] = nullptr; }
+  for (int i = 0; i < 2; i++)
+    if (ctx->aff_ev[i]) { cudaEventDestroy((cudaEvent_t)ctx->aff_ev[i]); ctx->aff_ev[i] = nullptr; }
+  rt::dev_free(ctx->aff_stats_dev);
+  ctx->aff_stats_dev = nullptr;
 #endif
   MsmScratch& m = ctx->msm;
   ctx->sort_scan.release();
   ctx->sort_hist.release();
   DevBuf* all[] = {&m.scalars, &m.bases, &m.keys_a, &m.keys_b, &m.vals_a, &m.vals_b, &m.sort_tmp, &m.bucket_start,
-                   &m.bucket_end, &m.task_meta, &m.partials, &m.seg_out, &m.win_out, &m.misc};
+                   &m.bucket_end, &m.task_meta, &m.partials, &m.seg_out, &m.win_out, &m.misc, &m.aff_a, &m.aff_b, &m.aff_pre,
+                   &m.aff_inv, &m.aff_off};
   for (DevBuf* b : all) b->release();
 }
 

@@ -341,8 +341,21 @@ int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* o
   return 0;
 }
 
+static int prove_products_impl(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                               double* timings_ms, bool literal_acc);
+
 int zkp_plonk_prove_products(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
                              double* timings_ms) {
+  return prove_products_impl(ctx, cc, blinding, out, timings_ms, false);
+}
+
+int zkp_plonk_prove_reference(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                              double* timings_ms) {
+  return prove_products_impl(ctx, cc, blinding, out, timings_ms, true);
+}
+
+static int prove_products_impl(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const uint64_t* blinding, zkp_plonk_proof* out,
+                               double* timings_ms, bool literal_acc) {
   if (!ctx || !cc || !blinding || !out) return ZKP_B200_ERR_INVALID_ARG;
   Timers tm;
   const size_t n = cc->size;
@@ -377,7 +390,25 @@ int zkp_plonk_prove_products(zkp_ctx* ctx, const zkp_plonk_compiled* cc, const u
   pre4w = mul_by_vanishing(pre4w, n);
   // compute_acc (prover.rs:302-377) from the domain evaluations kept at compile time
   std::vector<Fr> acc2(2 * n);
-  {
+  if (literal_acc) {
+    // prover.rs:302-377 as written: nine Horner evaluations of degree-n polynomials and one field division per row
+    // (O(n^2); the host-CPU baseline of bench.py and a third cross-check of the proof bytes at small n)
+    std::vector<Fr> roots(n);
+    roots[0] = Fr::one();
+    for (size_t i = 1; i < n; i++) roots[i] = roots[i - 1] * w;
+    Fr pre_acc = Fr::one();
+    acc2[0] = Fr::one();
+    for (size_t i = 1; i < n; i++) {
+      const Fr& x = roots[i - 1];
+      const Fr numerator = (eval(f_a, x) + beta * x + gamma) * (eval(f_b, x) + beta * cc->k1 * x + gamma) *
+                           (eval(f_c, x) + beta * cc->k2 * x + gamma);
+      const Fr denominator = (eval(f_a, x) + beta * eval(s1, x) + gamma) * (eval(f_b, x) + beta * eval(s2, x) + gamma) *
+                             (eval(f_c, x) + beta * eval(s3, x) + gamma);
+      pre_acc = pre_acc * numerator * fr_inv(denominator);
+      acc2[i] = pre_acc;
+    }
+    for (size_t i = 0; i < n; i++) acc2[n + i] = acc2[(i + 1) % n];  // rotate_left(1)
+  } else {
     std::vector<Fr> num(n), den(n), roots(n);
     roots[0] = Fr::one();
     for (size_t i = 1; i < n; i++) roots[i] = roots[i - 1] * w;

@@ -45,6 +45,7 @@ PLONK_ABI = {
     "zkp_plonk_compiled_poly": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "zkp_plonk_prove": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "zkp_plonk_prove_products": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "zkp_plonk_prove_reference": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "zkp_plonk_prove_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t,
                                                ctypes.c_size_t, _vp, _vp]),
     "zkp_plonk_numden_dev": (ctypes.c_int, [_vp, _vp]),
@@ -237,10 +238,13 @@ class Proof:
         return out + int(self.degree).to_bytes(8, "little")
 
 
-def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int], products: bool = False) -> Proof:
+def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int], products: bool = False,
+                   reference_acc: bool = False, timings: bool = True) -> Proof:
     """prover.rs:61-293 against the SRS resident on the compiled circuit's engine (`KzgScheme(engine, srs)`
     uploads it).  ``blinding`` = b1..b9.  ``products=True`` runs the cross-check prover that performs every
-    polynomial product of prover.rs separately (zkp_plonk_prove_products); both return the same bytes."""
+    polynomial product of prover.rs separately (zkp_plonk_prove_products); ``reference_acc=True`` additionally keeps
+    the reference's O(n^2) `compute_acc` (zkp_plonk_prove_reference); all return the same bytes.
+    ``timings=False`` passes no timing buffer: the prover then never synchronises the stream at phase boundaries."""
     eng = compiled_circuit.engine
     _bind(eng.lib)
     if len(blinding) != 9:
@@ -248,8 +252,10 @@ def generate_proof(compiled_circuit: CompiledCircuit, blinding: Sequence[int], p
     b = fields.fr_to_mont_array(blinding)
     ps = _ProofStruct()
     tm = (ctypes.c_double * 4)()
-    fn = eng.lib.zkp_plonk_prove_products if products else eng.lib.zkp_plonk_prove
-    _raise(eng, fn(eng._h, compiled_circuit._h, b.ctypes.data, ctypes.addressof(ps), ctypes.addressof(tm)))
+    fn = eng.lib.zkp_plonk_prove_reference if reference_acc else (
+        eng.lib.zkp_plonk_prove_products if products else eng.lib.zkp_plonk_prove)
+    _raise(eng, fn(eng._h, compiled_circuit._h, b.ctypes.data, ctypes.addressof(ps),
+                   ctypes.addressof(tm) if timings else None))
     cm = fields.g1_from_array(np.frombuffer(bytes(ps.commitments), dtype=np.uint64).reshape(9, 12))
     ev = fields.fr_from_mont_array(np.frombuffer(bytes(ps.evaluations), dtype=np.uint64).reshape(6, 4))
     u = fields.fr_from_mont_array(np.frombuffer(bytes(ps.u), dtype=np.uint64).reshape(1, 4))[0]
