@@ -65,6 +65,13 @@ size_t zkp_plonk_compiled_size(const zkp_plonk_compiled* cc);
  * 9..11 = s_sigma_1..3). */
 int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* out /* size x 4 */);
 
+/* The verifier's preprocessed commitments -- `get_circuit_commitment` (verifier.rs:160-185, recomputed by every
+ * `verify`: 8 MSMs of size n) and `CommonPreprocessedInput::new` (common_preprocessed_input/cpi_parser.rs:76-106):
+ * commit(q_m), commit(q_l), commit(q_r), commit(q_o), commit(q_c), commit(s_sigma_1..3), in that order, as ONE batched
+ * MSM pipeline over the coefficient vectors that `zkp_plonk_compile` left in HBM.  The result is cached on the compiled
+ * circuit; refresh != 0 (or a resident SRS of a different length) recomputes it -- pass refresh after replacing the SRS. */
+int zkp_plonk_preprocess(zkp_ctx* ctx, zkp_plonk_compiled* cc, uint64_t out_xy[8][12], int refresh);
+
 /* prover::generate_proof (prover.rs:61-293) against the SRS resident in `ctx` (>= size + 3 points).
  * blinding: b1..b9 (9 x 4 u64, Montgomery).  timings_ms (may be NULL; when given, the stream is synchronised at the
  * phase boundaries so the split is exact): [0] total, [1] commitments (MSM), [2] transforms (NTT / products),

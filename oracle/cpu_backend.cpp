@@ -90,6 +90,15 @@ int zkp_msm_g1(zkp_ctx* c, const uint64_t* scalars, size_t n, uint64_t out_xy[12
   return 0;
 }
 
+int zkp_msm_g1_multi_dev(zkp_ctx* c, uint32_t count, const void* const* scalars, const size_t* lens, uint64_t* out_xy,
+                         uint8_t* out_infinity) {
+  for (uint32_t j = 0; j < count; j++) {
+    const int st = zkp_msm_g1(c, (const uint64_t*)scalars[j], lens[j], out_xy + 12 * j, out_infinity ? out_infinity + j : nullptr);
+    if (st) return st;
+  }
+  return 0;
+}
+
 int zkp_g1_mul_srs0(zkp_ctx* c, const uint64_t* scalars, uint32_t count, uint64_t* out_xy) {  // scheme.rs:78-82
   if (!c || c->srs_len == 0) return ERR_SRS_TOO_SMALL;
   for (uint32_t k = 0; k < count; k++) orc_msm_naive(scalars + 4 * k, c->srs.data(), 1, out_xy + 12 * k);
@@ -149,7 +158,6 @@ int zkp_fr_mul_pointwise_dev(zkp_ctx*, void*, const void*, size_t) { return ERR_
 int zkp_fr_scan_dev(zkp_ctx*, void*, size_t, int, int) { return ERR_UNSUPPORTED; }
 int zkp_fr_trimmed_len_dev(zkp_ctx*, const void*, size_t, size_t*) { return ERR_UNSUPPORTED; }
 int zkp_g1_fold_partials(const uint64_t*, size_t, uint64_t*, uint8_t*) { return ERR_UNSUPPORTED; }
-int zkp_msm_g1_multi_dev(zkp_ctx*, uint32_t, const void* const*, const size_t*, uint64_t*, uint8_t*) { return ERR_UNSUPPORTED; }
 int zkp_msm_g1_multi_partial_dev(zkp_ctx*, uint32_t, const void* const*, const size_t*, uint64_t*) { return ERR_UNSUPPORTED; }
 int zkp_plonk_numden_dev(zkp_ctx*, const zkp_plonk_numden_args*) { return ERR_UNSUPPORTED; }
 int zkp_plonk_quotient_dev(zkp_ctx*, const zkp_plonk_quotient_args*) { return ERR_UNSUPPORTED; }

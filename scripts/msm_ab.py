@@ -12,6 +12,15 @@ import zkp_implementation_b200 as z  # noqa: E402
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 rounds_list = [int(x) for x in sys.argv[2:]] or [0, -1]
 n = 1 << log_n
+if os.environ.get("ZKP_L2_FETCH"):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    print("cudaDeviceSetLimit(MaxL2FetchGranularity) ->", rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["ZKP_L2_FETCH"]))))
+    v = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+    print("granularity now", v.value)
 eng = z.Engine(0, lib_path=os.environ.get("ZKP_LIB"))
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 eng.set_profiling(True)

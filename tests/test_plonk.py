@@ -212,3 +212,31 @@ def test_srs_too_small(zkp, engine):
         with pytest.raises(zkp.plonk.PlonkPanic) as ei:
             zkp.plonk.generate_proof(cc, BLIND, products=products)
         assert ei.value.status == 4
+
+
+@pytest.mark.parametrize("name", ["circuit_accepted_01", "circuit_accepted_02", "circuit_accepted_03"])
+def test_preprocess_commitments(zkp, engine, coracle, pyref, name):
+    """zkp_plonk_preprocess: the verifier's eight preprocessed commitments (verifier.rs:160-185, cpi_parser.rs:76-106)
+    as one batched MSM == the reference's per-polynomial `scheme.commit` restated literally (orc_msm_naive) on the
+    reference's own three circuits; cached, and recomputed when the SRS changes."""
+    F = zkp.fields
+    rc = getattr(ref, name)()
+    cc_ref = rc.compile()
+    cc = _native_circuit(zkp, rc).compile(engine)
+    srs = zkp.Srs.new_from_secret(engine, SECRET, cc.size)
+    zkp.KzgScheme(engine, srs)
+    limbs = srs.g1_limbs()
+    got = cc.preprocess()
+    ref_polys = {"q_m": cc_ref.g["qm"], "q_l": cc_ref.g["ql"], "q_r": cc_ref.g["qr"], "q_o": cc_ref.g["qo"], "q_c": cc_ref.g["qc"],
+                 "s_sigma_1": cc_ref.sigma[0], "s_sigma_2": cc_ref.sigma[1], "s_sigma_3": cc_ref.sigma[2]}
+    assert list(got) == list(zkp.plonk.CompiledCircuit.PREPROCESSED)
+    for k, poly in ref_polys.items():
+        want = F.g1_from_array(coracle.msm_naive(F.fr_to_mont_array(poly), limbs[:len(poly)]))[0] if poly else None
+        assert got[k] == want, k
+    assert cc.preprocess() == got  # served from the cache
+    srs2 = zkp.Srs.new_from_secret(engine, SECRET + 1, cc.size)
+    zkp.KzgScheme(engine, srs2)
+    other = cc.preprocess(refresh=True)
+    assert other != got and other["q_l"] == F.g1_from_array(
+        coracle.msm_naive(F.fr_to_mont_array(ref_polys["q_l"]), srs2.g1_limbs()[:len(ref_polys["q_l"])]))[0]
+    cc.close()

@@ -198,6 +198,10 @@ struct zkp_plonk_compiled {
   Fr* d_work = nullptr;         // prover workspace (see Work below)
   size_t work_elems = 0;
   std::mutex prove_mu;          // one proof at a time per compiled circuit: the workspace is shared
+  // verifier-side preprocessed commitments (q_m q_l q_r q_o q_c s1 s2 s3), cached after the first zkp_plonk_preprocess
+  bool pre_valid = false;
+  size_t pre_srs_len = 0;
+  uint64_t pre_xy[8][12];
   ~zkp_plonk_compiled() {
     if (ctx) {
       zkp_dev_free(ctx, d_vals);
@@ -332,6 +336,31 @@ int zkp_plonk_compile(zkp_ctx* ctx, const zkp_plonk_circuit* c, zkp_plonk_compil
 }
 
 void zkp_plonk_compiled_free(zkp_plonk_compiled* cc) { delete cc; }
+
+// verifier.rs:160-185 `get_circuit_commitment` / cpi_parser.rs:76-106 `CommonPreprocessedInput::new`: the eight
+// commitments every `verify` of the reference recomputes (8 MSMs of size n).  Here: ONE batched pipeline over the
+// coefficient vectors already resident in HBM, cached on the compiled circuit.
+int zkp_plonk_preprocess(zkp_ctx* ctx, zkp_plonk_compiled* cc, uint64_t out_xy[8][12], int refresh) {
+  if (!ctx || !cc || !out_xy) return ZKP_B200_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(cc->prove_mu);
+  const size_t srs_len = zkp_srs_len(ctx);
+  if (refresh || !cc->pre_valid || cc->pre_srs_len != srs_len) {
+    static const int which[8] = {6, 3, 4, 5, 7, 9, 10, 11};  // compiled polynomial indices of q_m q_l q_r q_o q_c s1 s2 s3
+    const void* ptrs[8];
+    size_t lens[8];
+    for (int k = 0; k < 8; k++) {
+      ptrs[k] = cc->d_coef + (size_t)which[k] * cc->size;
+      lens[k] = cc->poly[which[k]].size();  // DensePolynomial: trimmed coefficient count (scheme.rs:84-96 zips over it)
+      if (lens[k] > srs_len) return ZKP_B200_ERR_SRS_TOO_SMALL;
+    }
+    uint8_t inf[8];
+    PLONK_TRY(zkp_msm_g1_multi_dev(ctx, 8, ptrs, lens, &cc->pre_xy[0][0], inf));
+    cc->pre_valid = true;
+    cc->pre_srs_len = srs_len;
+  }
+  memcpy(out_xy, cc->pre_xy, sizeof(cc->pre_xy));
+  return 0;
+}
 size_t zkp_plonk_compiled_size(const zkp_plonk_compiled* cc) { return cc ? cc->size : 0; }
 
 int zkp_plonk_compiled_poly(const zkp_plonk_compiled* cc, int which, uint64_t* out) {

@@ -43,6 +43,7 @@ PLONK_ABI = {
     "zkp_plonk_compiled_free": (None, [_vp]),
     "zkp_plonk_compiled_size": (ctypes.c_size_t, [_vp]),
     "zkp_plonk_compiled_poly": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "zkp_plonk_preprocess": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "zkp_plonk_prove": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "zkp_plonk_prove_products": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "zkp_plonk_prove_reference": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
@@ -176,6 +177,15 @@ class CompiledCircuit:
         while c and c[-1] == 0:
             c.pop()
         return c
+
+    PREPROCESSED = ("q_m", "q_l", "q_r", "q_o", "q_c", "s_sigma_1", "s_sigma_2", "s_sigma_3")
+
+    def preprocess(self, refresh: bool = False) -> dict:
+        """`get_circuit_commitment` (verifier.rs:160-185) / `CommonPreprocessedInput::new` (cpi_parser.rs:76-106): the eight
+        selector / permutation commitments as one batched MSM, cached on the compiled circuit."""
+        out = np.zeros((8, 12), dtype=np.uint64)
+        _raise(self.engine, self.engine.lib.zkp_plonk_preprocess(self.engine._h, self._h, out.ctypes.data, 1 if refresh else 0))
+        return dict(zip(self.PREPROCESSED, fields.g1_from_array(out)))
 
     def close(self) -> None:
         if self._h:
