@@ -47,6 +47,15 @@ enum {
 /* ---- context ------------------------------------------------------------------------------- */
 /* Created once next to `KzgScheme::new(srs)` (kzg/src/scheme.rs:34). */
 int zkp_ctx_create(zkp_ctx** out, int device);
+/* Single-process multi-GPU context: the one `KzgScheme` value of the reference (kzg/src/scheme.rs:34, `&self` at :49-52)
+ * backed by `n_devices` GPUs, no torch / MPI in between.  The context runs everything on device_ids[0] except the
+ * hot path of the kzg crate: the resident SRS (zkp_srs_upload / zkp_srs_generate[_range]) is split by point range over
+ * the devices, zkp_srs_precompute builds one window table per device, and every commitment (zkp_msm_g1, zkp_msm_g1_dev
+ * and zkp_msm_g1_multi_dev with bases = resident SRS) runs one Pippenger per device on its point range, concurrently
+ * (one host thread per device), with the 192-byte partial sums folded on the host.  Device-resident scalars live on
+ * device_ids[0] and are copied to the peers over NVLink.  A device id may repeat (several shards on one GPU). */
+int zkp_ctx_create_multi(zkp_ctx** out, const int* device_ids, int n_devices);
+int zkp_ctx_shards(const zkp_ctx* ctx); /* 1 for a plain context */
 void zkp_ctx_destroy(zkp_ctx* ctx);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
 int zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);

@@ -27,6 +27,8 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 # name -> (restype, argtypes); every symbol include/zkp_b200.h declares
 ABI = {
     "zkp_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "zkp_ctx_create_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int]),
+    "zkp_ctx_shards": (ctypes.c_int, [ctypes.c_void_p]),
     "zkp_ctx_destroy": (None, [ctypes.c_void_p]),
     "zkp_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
@@ -141,10 +143,18 @@ def _ptr(a) -> ctypes.c_void_p:
 class Engine:
     """One context = one GPU + one CUDA stream (``zkp_ctx``)."""
 
-    def __init__(self, device: int = 0, lib_path: Optional[str] = None, stream: Optional[int] = None):
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None, stream: Optional[int] = None,
+                 devices: Optional[Sequence[int]] = None):
+        """``devices``: single-process multi-GPU context (zkp_ctx_create_multi): the resident SRS is sharded by point range
+        over these devices and every commitment against it runs on all of them; everything else runs on devices[0]."""
         self.lib = load_library(lib_path)
         h = ctypes.c_void_p()
-        st = self.lib.zkp_ctx_create(ctypes.byref(h), int(device))
+        if devices is not None:
+            ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            st = self.lib.zkp_ctx_create_multi(ctypes.byref(h), ctypes.cast(ids, ctypes.c_void_p), len(devices))
+            device = int(devices[0])
+        else:
+            st = self.lib.zkp_ctx_create(ctypes.byref(h), int(device))
         self._h = h if st == 0 else None
         self._check(st)
         self.device = device
@@ -166,6 +176,9 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def shards(self) -> int:
+        return int(self.lib.zkp_ctx_shards(self._h))
 
     def is_cuda(self) -> bool:
         """False for the CPU kernel emulator of the test-suite (tests/emu)."""

@@ -6,6 +6,8 @@
 
 #include "../../include/zkp_b200.h"
 #include "../../include/zkp_plonk.h"
+#include <thread>
+
 #include "engine.h"
 #include "poly.h"
 
@@ -13,6 +15,15 @@ using namespace zkp;
 
 struct zkp_ctx {
   Ctx c;
+  // Single-process multi-GPU context (zkp_ctx_create_multi): this object is shard 0, `peers` are the contexts of the
+  // other devices.  The resident SRS is split by point range (shard g holds [shard_lo[g], shard_lo[g + 1])); every
+  // commitment against it runs on all shards at once and the partial sums are folded on the host.
+  std::vector<zkp_ctx*> peers;
+  std::vector<size_t> shard_lo;
+  size_t srs_total = 0;
+  bool multi() const { return !peers.empty(); }
+  size_t nshards() const { return peers.size() + 1; }
+  zkp_ctx* shard(size_t g) { return g == 0 ? this : peers[g - 1]; }
 };
 
 namespace zkp {
@@ -92,8 +103,44 @@ int zkp_ctx_create(zkp_ctx** out, int device) {
   return ZKP_OK;
 }
 
+int zkp_ctx_create_multi(zkp_ctx** out, const int* device_ids, int n_devices) {
+  if (!out || !device_ids || n_devices < 1 || n_devices > 16) return ZKP_ERR_INVALID_ARG;
+  *out = nullptr;
+  zkp_ctx* h = nullptr;
+  ZKP_TRY(zkp_ctx_create(&h, device_ids[0]));
+  for (int g = 1; g < n_devices; g++) {
+    zkp_ctx* p = nullptr;
+    const int st = zkp_ctx_create(&p, device_ids[g]);
+    if (st != ZKP_OK) {
+      zkp_ctx_destroy(h);
+      return st;
+    }
+    h->peers.push_back(p);
+  }
+#ifndef ZKP_EMU
+  // peer access where the topology offers it (NVLink / NVSwitch); copies fall back to staging otherwise
+  for (int a = 0; a < n_devices; a++)
+    for (int b = 0; b < n_devices; b++) {
+      int can = 0;
+      if (device_ids[a] == device_ids[b]) continue;
+      if (cudaDeviceCanAccessPeer(&can, device_ids[a], device_ids[b]) == cudaSuccess && can) {
+        cudaSetDevice(device_ids[a]);
+        if (cudaDeviceEnablePeerAccess(device_ids[b], 0) != cudaSuccess) cudaGetLastError();  // already enabled
+      }
+    }
+  cudaSetDevice(device_ids[0]);
+#endif
+  h->shard_lo.assign((size_t)n_devices + 1, 0);
+  *out = h;
+  return ZKP_OK;
+}
+
+int zkp_ctx_shards(const zkp_ctx* h) { return h ? (int)(h->peers.size() + 1) : 0; }
+
 void zkp_ctx_destroy(zkp_ctx* h) {
   if (!h) return;
+  for (zkp_ctx* p : h->peers) zkp_ctx_destroy(p);
+  h->peers.clear();
   rt::set_device(h->c.device);
   rt::sync(h->c.stream);
   ntt_destroy(&h->c);
@@ -188,8 +235,50 @@ static int srs_alloc(Ctx* c, size_t n) {
   return ZKP_OK;
 }
 
+// point range of every shard: contiguous, the first n % G shards hold one extra point (dist.shard_range)
+static void split_srs(zkp_ctx* h, size_t n) {
+  const size_t G = h->nshards();
+  h->shard_lo.assign(G + 1, 0);
+  for (size_t g = 0; g < G; g++) h->shard_lo[g + 1] = h->shard_lo[g] + n / G + (g < n % G ? 1 : 0);
+  h->srs_total = n;
+}
+
+}  // extern "C" (templates need C++ linkage)
+// run fn(g) for every shard, peers on their own host threads (each sets its device); returns the first error
+template <class F>
+static int for_each_shard(zkp_ctx* h, F fn) {
+  const size_t G = h->nshards();
+  std::vector<int> st(G, ZKP_OK);
+#ifdef ZKP_EMU
+  for (size_t g = 0; g < G; g++) st[g] = fn(g);
+#else
+  std::vector<std::thread> th;
+  for (size_t g = 1; g < G; g++) th.emplace_back([&, g] { st[g] = fn(g); });
+  st[0] = fn(0);
+  for (auto& t : th) t.join();
+#endif
+  for (size_t g = 0; g < G; g++)
+    if (st[g] != ZKP_OK) return st[g];
+  return ZKP_OK;
+}
+extern "C" {
+
 int zkp_srs_upload(zkp_ctx* h, const uint64_t* xy, const uint8_t* infinity, size_t n) {
   if (!h || (n && !xy)) return ZKP_ERR_INVALID_ARG;
+  if (h->multi()) {
+    std::lock_guard<std::mutex> g0(h->c.mu);
+    split_srs(h, n);
+    return for_each_shard(h, [&](size_t g) {
+      zkp_ctx* s = h->shard(g);
+      std::unique_lock<std::mutex> lk(s->c.mu, std::defer_lock);
+      if (g) lk.lock();
+      const size_t lo = h->shard_lo[g], m = h->shard_lo[g + 1] - lo;
+      ZKP_TRY(rt::set_device(s->c.device));
+      ZKP_TRY(srs_alloc(&s->c, m));
+      ZKP_TRY(stage_affine(&s->c, xy + 12 * lo, infinity ? infinity + lo : nullptr, m, s->c.srs));
+      return rt::sync(s->c.stream);
+    });
+  }
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   ZKP_TRY(srs_alloc(&h->c, n));
@@ -206,10 +295,20 @@ int zkp_srs_upload_dev(zkp_ctx* h, const void* xy_dev, size_t n) {
   return rt::sync(h->c.stream);
 }
 
-size_t zkp_srs_len(const zkp_ctx* h) { return h ? h->c.srs_len : 0; }
+size_t zkp_srs_len(const zkp_ctx* h) { return h ? (h->multi() ? h->srs_total : h->c.srs_len) : 0; }
 
 int zkp_srs_precompute(zkp_ctx* h, uint32_t window_bits) {
   if (!h) return ZKP_ERR_INVALID_ARG;
+  if (h->multi()) {
+    std::lock_guard<std::mutex> g0(h->c.mu);
+    return for_each_shard(h, [&](size_t g) {
+      zkp_ctx* s = h->shard(g);
+      std::unique_lock<std::mutex> lk(s->c.mu, std::defer_lock);
+      if (g) lk.lock();
+      ZKP_TRY(rt::set_device(s->c.device));
+      return msm_precompute_dev(&s->c, window_bits);
+    });
+  }
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   return msm_precompute_dev(&h->c, window_bits);
@@ -221,6 +320,23 @@ int zkp_srs_generate(zkp_ctx* h, const uint64_t secret[4], size_t n, uint64_t* x
 
 int zkp_srs_generate_range(zkp_ctx* h, const uint64_t secret[4], size_t first, size_t n, uint64_t* xy_out) {
   if (!h || !secret) return ZKP_ERR_INVALID_ARG;
+  if (h->multi()) {
+    std::lock_guard<std::mutex> g0(h->c.mu);
+    split_srs(h, n);
+    Fr sec;
+    memcpy(sec.v, secret, 32);
+    return for_each_shard(h, [&](size_t g) {
+      zkp_ctx* s = h->shard(g);
+      std::unique_lock<std::mutex> lk(s->c.mu, std::defer_lock);
+      if (g) lk.lock();
+      const size_t lo = h->shard_lo[g], m = h->shard_lo[g + 1] - lo;
+      ZKP_TRY(rt::set_device(s->c.device));
+      ZKP_TRY(srs_alloc(&s->c, m));
+      ZKP_TRY(gen_srs_dev(&s->c, sec, first + lo, m, s->c.srs));
+      if (xy_out) ZKP_TRY(rt::d2h(xy_out + 12 * lo, s->c.srs, m * sizeof(G1Affine), s->c.stream));
+      return rt::sync(s->c.stream);
+    });
+  }
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   ZKP_TRY(srs_alloc(&h->c, n));
@@ -244,6 +360,42 @@ static int msm_nolock(Ctx* c, const void* scalars_dev, const void* bases_dev, si
   return msm_run_dev(c, (const Fr*)scalars_dev, bases, n, acc);
 }
 
+// Multi-context commitment against the sharded resident SRS: shard g runs its Pippenger on scalars [lo_g, min(hi_g, n))
+// (copied from the host buffer, or across devices from the primary device's buffer), all shards at once; the XYZZ
+// partials are folded here (G - 1 additions).  The caller holds the primary context's mutex.
+static int msm_sharded_nolock(zkp_ctx* h, const void* scalars, bool on_host, size_t n, G1Xyzz* acc) {
+  if (n > h->srs_total) return ZKP_ERR_SRS_TOO_SMALL;
+  const size_t G = h->nshards();
+  std::vector<G1Xyzz> part(G, G1Xyzz::infinity());
+  if (!on_host) ZKP_TRY(rt::sync(h->c.stream));  // the primary stream may still be producing the scalars
+  ZKP_TRY(for_each_shard(h, [&](size_t g) {
+    zkp_ctx* s = h->shard(g);
+    const size_t lo = h->shard_lo[g], hi = h->shard_lo[g + 1] < n ? h->shard_lo[g + 1] : n;
+    if (lo >= hi) return (int)ZKP_OK;
+    std::unique_lock<std::mutex> lk(s->c.mu, std::defer_lock);
+    if (g) lk.lock();
+    Ctx* c = &s->c;
+    const size_t m = hi - lo;
+    ZKP_TRY(rt::set_device(c->device));
+    const uint8_t* src = (const uint8_t*)scalars + lo * sizeof(Fr);
+    const void* dev_scalars = src;
+    if (on_host || g) {  // shard 0 reads device scalars in place
+      ZKP_TRY(c->msm.scalars.reserve(m * sizeof(Fr)));
+      ZKP_TRY(on_host ? rt::h2d(c->msm.scalars.p, src, m * sizeof(Fr), c->stream)
+                      : rt::copy_any(c->msm.scalars.p, src, m * sizeof(Fr), c->stream));
+      dev_scalars = c->msm.scalars.p;
+    }
+    return msm_nolock(c, dev_scalars, nullptr, m, &part[g]);
+  }));
+  rt::set_device(h->c.device);
+  *acc = part[0];
+  for (size_t g = 1; g < G; g++) xyzz_add(*acc, part[g]);
+  uint32_t launches = 0;
+  for (size_t g = 0; g < G; g++) launches += h->shard(g)->c.msm_launches;
+  h->c.msm_launches = launches;
+  return ZKP_OK;
+}
+
 int zkp_msm_g1_partial_dev(zkp_ctx* h, const void* scalars_dev, const void* bases_dev, size_t n, uint64_t out_xyzz[24]) {
   if (!h || !out_xyzz || (n && !scalars_dev)) return ZKP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(h->c.mu);
@@ -260,7 +412,8 @@ int zkp_msm_g1_dev(zkp_ctx* h, const void* scalars_dev, const void* bases_dev, s
   std::lock_guard<std::mutex> g(h->c.mu);
   ZKP_TRY(rt::set_device(h->c.device));
   G1Xyzz acc;
-  ZKP_TRY(msm_nolock(&h->c, scalars_dev, bases_dev, n, &acc));
+  if (h->multi() && !bases_dev) ZKP_TRY(msm_sharded_nolock(h, scalars_dev, false, n, &acc));
+  else ZKP_TRY(msm_nolock(&h->c, scalars_dev, bases_dev, n, &acc));
   write_affine(acc, out_xy, out_infinity);
   return ZKP_OK;
 }
@@ -271,13 +424,24 @@ int zkp_msm_g1_multi_dev(zkp_ctx* h, uint32_t count, const void* const* scalars_
   std::lock_guard<std::mutex> g(h->c.mu);
   Ctx* c = &h->c;
   ZKP_TRY(rt::set_device(c->device));
+  G1Xyzz acc[16];
+  if (h->multi()) {  // one sharded commitment after the other (the batch pipeline is per device)
+    uint32_t launches = 0;
+    for (uint32_t j = 0; j < count; j++) {
+      if (lens[j] && !scalars_dev[j]) return ZKP_ERR_INVALID_ARG;
+      ZKP_TRY(msm_sharded_nolock(h, scalars_dev[j], false, lens[j], &acc[j]));
+      launches += c->msm_launches;
+    }
+    c->msm_launches = launches;
+    write_affine_batch(acc, count, out_xy, out_infinity);
+    return ZKP_OK;
+  }
   size_t shortest = (size_t)-1;
   for (uint32_t j = 0; j < count; j++) {
     if (lens[j] > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
     if (lens[j] && !scalars_dev[j]) return ZKP_ERR_INVALID_ARG;
     if (lens[j] < shortest) shortest = lens[j];
   }
-  G1Xyzz acc[16];
   if (count > 1 && c->srs_tab && shortest >= c->srs_len / 4) {
     ZKP_TRY(msm_run_multi_dev(c, (const Fr* const*)scalars_dev, lens, count, c->srs_tab, acc, c->srs_tab_c, c->srs_len));
   } else {
@@ -335,6 +499,12 @@ int zkp_msm_g1(zkp_ctx* h, const uint64_t* scalars, size_t n, uint64_t out_xy[12
   if (!h || !out_xy || (n && !scalars)) return ZKP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(h->c.mu);
   Ctx* c = &h->c;
+  if (h->multi()) {
+    G1Xyzz acc;
+    ZKP_TRY(msm_sharded_nolock(h, scalars, true, n, &acc));
+    write_affine(acc, out_xy, out_infinity);
+    return ZKP_OK;
+  }
   if (n > c->srs_len) return ZKP_ERR_SRS_TOO_SMALL;
   ZKP_TRY(rt::set_device(c->device));
   ZKP_TRY(c->msm.scalars.reserve(n * sizeof(Fr)));

@@ -31,6 +31,7 @@ inline void host_free_pinned(void* p) { free(p); }
 inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t) { if (bytes) memcpy(d, h, bytes); return ZKP_OK; }
 inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t) { if (bytes) memcpy(h, d, bytes); return ZKP_OK; }
 inline int d2d(void* dst, const void* src, size_t bytes, cudaStream_t) { if (bytes) memmove(dst, src, bytes); return ZKP_OK; }
+inline int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t) { if (bytes) memmove(dst, src, bytes); return ZKP_OK; }
 inline int dev_memset(void* d, int v, size_t bytes, cudaStream_t) { if (bytes) memset(d, v, bytes); return ZKP_OK; }
 inline int sync(cudaStream_t) { return ZKP_OK; }
 inline int check_last() { return ZKP_OK; }
@@ -68,6 +69,8 @@ inline void host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t s) { return bytes ? wrap(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)) : ZKP_OK; }
 inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t s) { return bytes ? wrap(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)) : ZKP_OK; }
 inline int d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) { return bytes ? wrap(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s)) : ZKP_OK; }
+// unified-addressing copy: source and destination may live on different devices (peer copy over NVLink when enabled)
+inline int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t s) { return bytes ? wrap(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s)) : ZKP_OK; }
 inline int dev_memset(void* d, int v, size_t bytes, cudaStream_t s) { return bytes ? wrap(cudaMemsetAsync(d, v, bytes, s)) : ZKP_OK; }
 inline int sync(cudaStream_t s) { return wrap(cudaStreamSynchronize(s)); }
 inline int check_last() { return wrap(cudaGetLastError()); }
