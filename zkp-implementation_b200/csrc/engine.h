@@ -72,8 +72,9 @@ struct Ctx {
   G1Affine* srs = nullptr;
   size_t srs_len = 0;
   // fixed-base table over the SRS (zkp_srs_precompute): window w = 2^(c w) * srs[i], w < srs_tab_windows
+  // Records are srs_tab_stride16 x 16 bytes apart: 6 (packed, the default) or 8 (128-byte records, -DZKP_TABLE_PADDED).
   G1Affine* srs_tab = nullptr;
-  uint32_t srs_tab_c = 0, srs_tab_windows = 0;
+  uint32_t srs_tab_c = 0, srs_tab_windows = 0, srs_tab_stride16 = 6;
   G1Affine* srs0_tab = nullptr;  // 32 x 256 byte-window table of srs[0] for commit_para (built on first use)
 
   // NTT state
@@ -142,7 +143,8 @@ int msm_precompute_dev(Ctx* ctx, uint32_t window_bits);
 // batched-affine tree rounds over the bucket-sorted point list (msm_affine.cu)
 uint32_t msm_affine_choose_rounds(size_t total, size_t total_buckets);
 size_t msm_affine_bound(size_t total, size_t nb, uint32_t rounds);
-int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, const G1Affine* bases, const uint32_t* bstart,
+int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, const G1Affine* bases, uint32_t base_stride16,
+                          const uint32_t* bstart,
                           const uint32_t* bend, uint32_t nb, size_t total, const G1Affine** pts, const uint32_t** off,
                           size_t* bound);
 

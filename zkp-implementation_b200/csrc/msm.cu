@@ -193,19 +193,22 @@ __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __r
 // DIRECT = true: the run is a slice of `bases` itself (the output of the batched-affine tree rounds, msm_affine.cu).
 template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks,
-                                                                     const uint32_t* __restrict__ order, uint32_t ntasks,
+                                                                     const uint32_t* __restrict__ order,
+                                                                     const uint32_t* __restrict__ ntasks_ptr,
                                                                      const uint32_t* __restrict__ svals,
-                                                                     const G1Affine* __restrict__ bases,
+                                                                     const G1Affine* __restrict__ bases, uint32_t stride16,
                                                                      G1Xyzz* __restrict__ partials) {
+  // The grid covers the host's upper bound of the task count; the real count stays on the device (no mid-pipeline
+  // read-back): the length-sorted order puts the zero-length padding slots last.
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= ntasks) return;
+  if (slot >= *ntasks_ptr) return;
   const uint32_t t = order[slot];  // longest runs first; partials stay in bucket order
   const MsmTask tk = tasks[t];
   const uint32_t* v = DIRECT ? nullptr : svals + tk.start;
   const G1Affine* run = bases + tk.start;
   G1Xyzz acc = G1Xyzz::infinity();
   uint32_t pv = DIRECT ? 0u : v[0];
-  G1Affine nxt = DIRECT ? ld_affine(run) : ld_affine(bases + (pv & ~SIGN_BIT));
+  G1Affine nxt = DIRECT ? ld_affine(run) : ld_affine_s(bases, pv & ~SIGN_BIT, stride16);
   for (uint32_t i = 0; i < tk.len; i++) {
     G1Affine cur = nxt;
     const uint32_t cv = pv;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTa
         nxt = ld_affine(run + i + 1);
       } else {
         pv = v[i + 1];
-        nxt = ld_affine(bases + (pv & ~SIGN_BIT));
+        nxt = ld_affine_s(bases, pv & ~SIGN_BIT, stride16);
       }
     }
     if (cv & SIGN_BIT) cur = g1_neg(cur);
@@ -379,6 +382,14 @@ __global__ void __launch_bounds__(32) msm_reduce_combine_kernel(const G1Xyzz* __
 }
 
 // 2^c * P for every point of one table window (fixed-base precomputation)
+// table window (records stride16 x 16 bytes apart) <- packed points
+__global__ void __launch_bounds__(256) msm_table_store_kernel(const G1Affine* __restrict__ in, size_t n, G1Affine* __restrict__ tab,
+                                                              size_t first, uint32_t stride16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_affine_s(tab, first + i, stride16, ld_affine(in + i));
+}
+
 __global__ void __launch_bounds__(128) msm_shift_window_kernel(const G1Affine* __restrict__ in, size_t n, uint32_t c,
                                                                G1Xyzz* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,6 +524,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ctx->msm_launches = 0;
   ctx->sort_launches = 0;
   const bool fixed = fixed_c != 0;
+  const uint32_t base_stride16 = fixed ? ctx->srs_tab_stride16 : 6u;  // only the fixed-base table has padded records
   if (count == 0) return ZKP_OK;
   if (!fixed && count != 1) return ZKP_ERR_INVALID_ARG;
   size_t n_sum = 0, n_max = 0;
@@ -615,7 +627,8 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   size_t total_fin = total;
   if (rounds) {
     const uint32_t* off = nullptr;
-    const int as = msm_affine_rounds_dev(ctx, rounds, svals, bases, bstart, bend, total_buckets, total, &run_pts, &off, &total_fin);
+    const int as = msm_affine_rounds_dev(ctx, rounds, svals, bases, base_stride16, bstart, bend, total_buckets, total, &run_pts,
+                                         &off, &total_fin);
     if (as == ZKP_ERR_OOM) {  // the round buffers do not fit next to the table: plain XYZZ accumulation
       rounds = 0;
       run_pts = nullptr;
@@ -645,6 +658,7 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   uint32_t* task_order = task_len_sorted + max_tasks;
   G1Xyzz* partials = m.partials.as<G1Xyzz>();
   // 4. tasks
+  ZKP_TRY(rt::dev_memset(task_len, 0, max_tasks * 2 * sizeof(uint32_t), st));  // lengths and ids of the padding slots
   ZKP_TRY(rt::dev_memset(ntask + total_buckets, 0, 4, st));
   ZKP_TRY(rt::dev_memset(heavy, 0, 4, st));
   ZKP_LAUNCH_NOSYNC(msm_task_count_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, run_start, run_end,
@@ -653,21 +667,22 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_LAUNCH_NOSYNC(msm_task_build_kernel, dim3((total_buckets + 255) / 256), dim3(256), 0, st, run_start, run_end, task_off,
              total_buckets, smax, tasks, task_len, task_id);
   ctx->msm_launches += 2;
-  uint32_t ntasks = 0;
-  ZKP_TRY(rt::d2h(&ntasks, task_off + total_buckets, 4, st));
-  ZKP_TRY(rt::sync(st));
-  // 5. accumulate (XYZZ finish)
-  if (ntasks) {
+  // 5. accumulate (XYZZ finish).  The number of tasks stays on the device (task_off[total_buckets]); the sort and the
+  // launch are sized by the bound max_tasks, with zero-length padding entries sorted to the end.
+  {
+    const uint32_t* ntasks_dev = task_off + total_buckets;
+    const uint32_t nslots = (uint32_t)max_tasks;
     uint32_t len_bits = 1;
     while ((1u << len_bits) <= smax) len_bits++;
     uint32_t *len_sorted = nullptr, *order = nullptr;
-    ZKP_TRY(sort_pairs(ctx, task_len, task_id, task_len_sorted, task_order, ntasks, len_bits, true, &len_sorted, &order));
+    ZKP_TRY(sort_pairs(ctx, task_len, task_id, task_len_sorted, task_order, nslots, len_bits, true, &len_sorted, &order));
     if (run_pts)
-      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<true>, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
-                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks, (const uint32_t*)nullptr, run_pts, partials);
+      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<true>, dim3((nslots + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
+                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks_dev, (const uint32_t*)nullptr, run_pts, 6u, partials);
     else
-      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<false>, dim3((ntasks + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
-                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks, (const uint32_t*)svals, bases, partials);
+      ZKP_LAUNCH_NOSYNC(msm_accumulate_kernel<false>, dim3((nslots + ACC_THREADS - 1) / ACC_THREADS), dim3(ACC_THREADS), 0, st,
+                        (const MsmTask*)tasks, (const uint32_t*)order, ntasks_dev, (const uint32_t*)svals, bases, base_stride16,
+                        partials);
     ctx->msm_launches += 1;
   }
   // 6. reduce: fold the partials of heavily split buckets, gather one value per bucket, then the bit-plane levels
@@ -745,17 +760,42 @@ int msm_precompute_dev(Ctx* ctx, uint32_t c) {
   if (c < 2 || c > 26) return ZKP_ERR_INVALID_ARG;
   const uint32_t nwin = 255 / c + 1;
   if ((size_t)nwin * n >= ((size_t)1 << 31)) return ZKP_ERR_INVALID_ARG;
-  ZKP_TRY(rt::dev_malloc((void**)&ctx->srs_tab, (size_t)nwin * n * sizeof(G1Affine)));
-  DevBuf tmp;
+  // Record layout: packed 96-byte records by default.  -DZKP_TABLE_PADDED switches to 128-byte records (a gathered point
+  // = exactly one 128-byte DRAM line instead of 1.5 on average).  Measured on B200 at 2^24 (profiles/r02_msm_affine_ab.txt):
+  // DRAM bytes of the first-round kernels drop as predicted but their time does not (73.7 vs 73.5 ms per MSM) -- the
+  // gathers are bound by the number of random line fetches over an 18 GiB table, not by bytes -- so the 6 GiB are not spent.
+  uint32_t stride16 = 6;
+#ifdef ZKP_TABLE_PADDED
+  stride16 = 8;
+#ifndef ZKP_EMU
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (size_t)nwin * n * 128 > total_b / 3) stride16 = 6;
+  }
+#endif
+#endif
+  ZKP_TRY(rt::dev_malloc((void**)&ctx->srs_tab, (size_t)nwin * n * stride16 * 16));
+  DevBuf tmp, win;
   int st = tmp.reserve(n * sizeof(G1Xyzz));
-  if (st == ZKP_OK) st = rt::d2d(ctx->srs_tab, ctx->srs, n * sizeof(G1Affine), ctx->stream);
+  if (st == ZKP_OK) st = win.reserve(2 * n * sizeof(G1Affine));  // previous / current window, packed
+  const unsigned sblocks = (unsigned)((n + 255) / 256);
+  const G1Affine* prev = ctx->srs;
+  if (st == ZKP_OK) {
+    if (stride16 == 8) st = rt::dev_memset(ctx->srs_tab, 0, (size_t)nwin * n * 128, ctx->stream);  // defined padding
+    ZKP_LAUNCH_NOSYNC(msm_table_store_kernel, dim3(sblocks), dim3(256), 0, ctx->stream, prev, n, ctx->srs_tab, (size_t)0, stride16);
+  }
   for (uint32_t w = 1; w < nwin && st == ZKP_OK; w++) {
-    ZKP_LAUNCH_NOSYNC(msm_shift_window_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, ctx->stream,
-               (const G1Affine*)(ctx->srs_tab + (size_t)(w - 1) * n), n, c, tmp.as<G1Xyzz>());
-    st = normalise_dev(ctx, tmp.as<G1Xyzz>(), n, ctx->srs_tab + (size_t)w * n);
+    G1Affine* cur = win.as<G1Affine>() + (size_t)(w & 1) * n;
+    ZKP_LAUNCH_NOSYNC(msm_shift_window_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, ctx->stream, prev, n, c,
+               tmp.as<G1Xyzz>());
+    st = normalise_dev(ctx, tmp.as<G1Xyzz>(), n, cur);
+    ZKP_LAUNCH_NOSYNC(msm_table_store_kernel, dim3(sblocks), dim3(256), 0, ctx->stream, (const G1Affine*)cur, n, ctx->srs_tab,
+                      (size_t)w * n, stride16);
+    prev = cur;
   }
   if (st == ZKP_OK) st = rt::sync(ctx->stream);
   tmp.release();
+  win.release();
   if (st != ZKP_OK) {
     rt::dev_free(ctx->srs_tab);
     ctx->srs_tab = nullptr;
@@ -763,6 +803,7 @@ int msm_precompute_dev(Ctx* ctx, uint32_t c) {
   }
   ctx->srs_tab_c = c;
   ctx->srs_tab_windows = nwin;
+  ctx->srs_tab_stride16 = stride16;
   return ZKP_OK;
 }
 

@@ -44,6 +44,7 @@ struct AffRound {
   uint32_t nb;
   const uint32_t* svals;    // first round: sorted (point index | sign << 31); later rounds: null
   const G1Affine* in;       // first round: the bases / fixed-base table; later rounds: the previous round's output
+  uint32_t in_stride16;     // first round: record stride of `in` in 16-byte words (6 packed, 8 padded table)
   G1Affine* out;
   Fq* pre;                  // [M_out] exclusive prefix products of the denominators (per thread)
   Fq* tot;                  // [ceil(M_out / K)] per-thread products
@@ -95,23 +96,6 @@ __device__ __forceinline__ void aff_walk(const AffRound& a, uint32_t o0, uint32_
   }
 }
 
-template <bool FIRST>
-__device__ __forceinline__ Fq aff_ld_x(const AffRound& a, uint32_t pos) {
-  if (FIRST) return ld_fq(&a.in[a.svals[pos] & ~AFF_SIGN].x);
-  return ld_fq(&a.in[pos].x);
-}
-
-template <bool FIRST>
-__device__ __forceinline__ G1Affine aff_ld(const AffRound& a, uint32_t pos) {
-  if (FIRST) {
-    const uint32_t v = a.svals[pos];
-    G1Affine p = ld_affine(a.in + (v & ~AFF_SIGN));
-    if (v & AFF_SIGN) p = g1_neg(p);
-    return p;
-  }
-  return ld_affine(a.in + pos);
-}
-
 enum { AFF_GENERAL = 0, AFF_DOUBLE = 1, AFF_IS_P1 = 2, AFF_IS_P2 = 3, AFF_IS_INF = 4 };
 
 __device__ __forceinline__ int aff_classify(const G1Affine& p1, const G1Affine& p2) {
@@ -143,14 +127,16 @@ __device__ __forceinline__ void aff_refs(const AffRound& a, const uint32_t (&idx
 
 template <bool FIRST>
 __device__ __forceinline__ G1Affine aff_ld_ref(const AffRound& a, uint32_t ref) {
-  G1Affine p = ld_affine(a.in + (FIRST ? (ref & ~AFF_SIGN) : ref));
-  if (FIRST && (ref & AFF_SIGN)) p = g1_neg(p);
+  if (!FIRST) return ld_affine(a.in + ref);
+  G1Affine p = ld_affine_s(a.in, ref & ~AFF_SIGN, a.in_stride16);
+  if (ref & AFF_SIGN) p = g1_neg(p);
   return p;
 }
 
 template <bool FIRST>
 __device__ __forceinline__ Fq aff_ld_ref_x(const AffRound& a, uint32_t ref) {
-  return ld_fq(&a.in[FIRST ? (ref & ~AFF_SIGN) : ref].x);
+  if (!FIRST) return ld_fq(&a.in[ref].x);
+  return ld_affine_x_s(a.in, ref & ~AFF_SIGN, a.in_stride16);
 }
 
 // ---- A: denominators ------------------------------------------------------------------------------
@@ -312,7 +298,8 @@ static unsigned aff_blocks(size_t items) { return (unsigned)((items + AFF_THREAD
 // Runs `rounds` tree rounds over the bucket-sorted (point | sign) list.  On return *pts is the device array holding the
 // shortened runs and *off its run starts ([nb + 1] entries, off[nb] = number of points), *bound an upper bound of that
 // number.  Returns ZKP_ERR_OOM without side effects when the buffers do not fit (the caller falls back to rounds = 0).
-int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, const G1Affine* bases, const uint32_t* bstart,
+int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, const G1Affine* bases, uint32_t base_stride16,
+                          const uint32_t* bstart,
                           const uint32_t* bend, uint32_t nb, size_t total, const G1Affine** pts, const uint32_t** off,
                           size_t* bound) {
   MsmScratch& m = ctx->msm;
@@ -366,6 +353,7 @@ int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, cons
     a.nb = nb;
     a.svals = (r == 0) ? svals : nullptr;
     a.in = in;
+    a.in_stride16 = (r == 0) ? base_stride16 : 6u;
     a.out = out;
     a.pre = m.aff_pre.as<Fq>();
     a.stats = nullptr;
