@@ -348,6 +348,14 @@ def run_engine(args) -> None:
 
     aff = eng.last_affine_profile()
     extra = {}
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": "g1_msm_2p24_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "e2e_ms": e2e_ms, "gpu_launches": timed_launches, "phases_ms": phases,
+                              "affine": aff, "quick": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if rank == 0:
         # ---- the other numbers BASELINE.json names, N = 1 semantics on rank 0's GPU ----
         n20 = 1 << 20
@@ -670,6 +678,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--quick", action="store_true",
+                    help="headline step only (no `extra`, no CPU legs): the command profiled under ncu for profiles/")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
