@@ -30,6 +30,14 @@ def test_field_ops(hostlib, zkp, name):
                         (7, a * b * rinv % mod)):
             assert fn(op, _pack(a, n), _pack(b, n), out) == 0
             assert _unpack(out) == exp, (name, op, hex(a), hex(b))
+    # dedicated squaring (triangular carry-chain rows): edge values with every top / bottom bit pattern, then random
+    sq = [0, 1, 2, mod - 1, mod - 2, R % mod, (1 << 31), (1 << 32) - 1, (1 << 63) | 1, mod >> 1, (mod >> 1) + 1,
+          int("55" * (4 * n), 16) % mod, int("aa" * (4 * n), 16) % mod, int("ff" * (4 * n), 16) % mod,
+          int("80000000" * n, 16) % mod, int("7fffffff" * n, 16) % mod]
+    sq += [rnd.randrange(mod) for _ in range(20000)]
+    for a in sq if name == "fq" else []:  # Fq only: 3p < 2^384 (the rows' partial sums fit); Fr squares through fp_mul
+        assert fn(8, _pack(a, n), None, out) == 0
+        assert _unpack(out) == a * a * rinv % mod, (name, "sqr", hex(a))
     a = rnd.randrange(1, mod)
     fn(4, _pack(a * R % mod, n), None, out)
     assert _unpack(out) == pow(a, -1, mod) * R % mod

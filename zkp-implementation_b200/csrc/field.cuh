@@ -80,6 +80,7 @@ ZKP_PTX3(madc_hi, "madc.hi.u32", return (uint32_t)(((uint64_t)a * b) >> 32) + c 
 // ------------------------------------------------------------------------------------------------
 struct FrParams {
   static constexpr int N = 8;
+  static constexpr bool DEDICATED_SQR = false;  // 3r > 2^256: the squaring rows' partial sums would not fit 8 limbs
   // r = ...ffffffff00000001: limb 0 is 1, limb 1 is 2^32 - 1 and -r^-1 = -1 (mod 2^32), so in every
   // Montgomery reduction step m = -t0, m * r[0] is an addition and m * r[1] = (m << 32) - m is two ALU
   // ops: 6 instead of 8 multiply-adds per step (112 instead of 128 per product).
@@ -108,6 +109,7 @@ struct FrParams {
 
 struct FqParams {
   static constexpr int N = 12;
+  static constexpr bool DEDICATED_SQR = true;   // 3p < 2^383: see fp_sqr_chain
   static constexpr bool LOW_LIMBS_SPECIAL = false;
   static constexpr uint32_t M0 = 0xfffcfffdu;  // -p^-1 mod 2^32
   ZKP_HD static constexpr uint32_t mod(int i) {
@@ -425,6 +427,131 @@ ZKP_HD Fp<P> fp_mul_chain(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---- dedicated squaring in the same carry-chain form ---------------------------------------------------
+// a^2 = sum_i a_i^2 2^(64 i) + 2 sum_{i<j} a_i a_j 2^(32 (i+j)).  Row i of the interleaved (CIOS) schedule multiplies
+// the scalar a_i by the vector  u_i = [a_i, 2 a_(i+1), 2 a_(i+2), ...]  -- the doubled higher limbs, with the bit
+// shifted across limb boundaries -- and skips the limbs below i (their products were added, doubled, by rows j < i).
+// Everything at limb position k has been added by row k, which is what the interleaved reduction needs.  Row i costs
+// n - i products instead of n: n (n + 1) / 2 + n^2 limb products per squaring instead of 2 n^2 (222 instead of 288 for
+// Fq); the skipped products become add-with-carry instructions that keep the carry chain and the per-row shift alive.
+// The partial sums run ahead of the plain schedule (row i adds the DOUBLED cross terms of a_i at once), so the accumulator
+// is bounded by 2a + p < 3p instead of a + p: the modulus must satisfy 3p < 2^(32 n) -- true for Fq (p < 2^381), not for Fr
+// (r ~ 0.45 * 2^256), which keeps fp_mul(a, a) (P::DEDICATED_SQR; the NTT has no squarings anyway).
+namespace detail {
+// odd[j] = u[j]*bi + odd[j+2] for the products at or above index `skip` (index into the ODD-limb vector `a`, i.e. limb
+// 1 + j of the row vector), plain carry propagation below; carry-in from CC.CF
+template <int n>
+ZKP_HD void madc_n_rshift_from(uint32_t* odd, const uint32_t* a, uint32_t bi, int skip) {
+#pragma unroll
+  for (int j = 0; j < n - 2; j += 2) {
+    if (j + 1 >= skip) {
+      odd[j] = ptx::madc_lo_cc(a[j], bi, odd[j + 2]);
+      odd[j + 1] = ptx::madc_hi_cc(a[j], bi, odd[j + 3]);
+    } else {
+      odd[j] = ptx::addc_cc(odd[j + 2], 0u);
+      odd[j + 1] = ptx::addc_cc(odd[j + 3], 0u);
+    }
+  }
+  if (n - 1 >= skip) {
+    odd[n - 2] = ptx::madc_lo_cc(a[n - 2], bi, 0u);
+    odd[n - 1] = ptx::madc_hi(a[n - 2], bi, 0u);
+  } else {
+    odd[n - 2] = ptx::addc_cc(0u, 0u);
+    odd[n - 1] = 0u;
+  }
+}
+// acc += a[even j]*bi for j >= skip along one carry chain (lower pairs untouched); carry-out left in CC.CF
+template <int n>
+ZKP_HD void cmad_n_from(uint32_t* acc, const uint32_t* a, uint32_t bi, int skip) {
+  bool started = false;
+#pragma unroll
+  for (int j = 0; j < n; j += 2) {
+    if (j < skip) continue;
+    if (!started) {
+      acc[j] = ptx::mad_lo_cc(a[j], bi, acc[j]);
+      started = true;
+    } else {
+      acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+    }
+    acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+  }
+  if (!started) ptx::add_cc(0u, 0u);  // clears CC.CF: the caller's closing addc must see no carry
+}
+
+// one row of the squaring: `row` is this row's index i (limbs below i are skipped), u the row vector (n + 1 entries)
+template <class P>
+ZKP_HD void sqr_row_redc(uint32_t* even, uint32_t* odd, const uint32_t* u, uint32_t bi, const uint32_t* mod, int row) {
+  constexpr int n = P::N;
+  if (row == 0) {
+    mul_n<n>(odd, u + 1, bi);
+    mul_n<n>(even, u, bi);
+  } else {
+    even[0] = ptx::add_cc(even[0], odd[1]);
+    madc_n_rshift_from<n>(odd, u + 1, bi, row);
+    cmad_n_from<n>(even, u, bi, row);
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  }
+  if constexpr (P::LOW_LIMBS_SPECIAL) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t mi = even[0] * zkp_opaque_minus_one;
+#else
+    const uint32_t mi = 0u - even[0];
+#endif
+    const uint32_t lo1 = 0u - mi;
+    const uint32_t hi1 = mi - (mi != 0u ? 1u : 0u);
+    odd[0] = ptx::add_cc(odd[0], lo1);
+    odd[1] = ptx::addc_cc(odd[1], hi1);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+      odd[j] = ptx::madc_lo_cc(mod[j + 1], mi, odd[j]);
+      odd[j + 1] = ptx::madc_hi_cc(mod[j + 1], mi, odd[j + 1]);
+    }
+    even[0] = ptx::add_cc(even[0], mi);
+    even[1] = ptx::addc_cc(even[1], 0u);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+      even[j] = ptx::madc_lo_cc(mod[j], mi, even[j]);
+      even[j + 1] = ptx::madc_hi_cc(mod[j], mi, even[j + 1]);
+    }
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  } else {
+    const uint32_t mi = even[0] * P::M0;
+    cmad_n<n>(odd, mod + 1, mi);
+    cmad_n<n>(even, mod, mi);
+    odd[n - 1] = ptx::addc(odd[n - 1], 0u);
+  }
+}
+}  // namespace detail
+
+template <class P>
+ZKP_HD Fp<P> fp_sqr_chain(const Fp<P>& a) {
+  constexpr int n = P::N;
+  uint32_t even[n], odd[n];
+  detail::ModLimbs<P> M;
+  // 2a, limb by limb (the top limb has spare bits: nothing is shifted out)
+  uint32_t a2[n];
+  a2[0] = a.v[0] << 1;
+#pragma unroll
+  for (int i = 1; i < n; i++) a2[i] = (a.v[i] << 1) | (a.v[i - 1] >> 31);
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    // row vector u_i: limb i = a_i, limb i + 1 = a_(i+1) << 1 (a_i's top bit belongs to the skipped part), above = a2
+    uint32_t u[n + 1];
+#pragma unroll
+    for (int j = 0; j < n; j++) u[j] = (j < i) ? 0u : (j == i ? a.v[j] : (j == i + 1 ? (a.v[j] << 1) : a2[j]));
+    u[n] = 0;
+    if ((i & 1) == 0) detail::sqr_row_redc<P>(even, odd, u, a.v[i], M.m, i);
+    else detail::sqr_row_redc<P>(odd, even, u, a.v[i], M.m, i);
+  }
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) r.v[i] = ptx::addc_cc(even[i], odd[i + 1]);
+  r.v[n - 1] = ptx::addc(even[n - 1], 0u);
+  fp_final_sub(r);
+  return r;
+}
+
 template <class P>
 ZKP_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if ZKP_PTX_DEVICE || defined(ZKP_FIELD_CHAIN_ON_HOST)
@@ -438,6 +565,9 @@ ZKP_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 
 template <class P>
 ZKP_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#if (ZKP_PTX_DEVICE || defined(ZKP_FIELD_CHAIN_ON_HOST)) && !defined(ZKP_NO_DEDICATED_SQR)
+  if constexpr (P::DEDICATED_SQR) return fp_sqr_chain(a);
+#endif
   return fp_mul(a, a);
 }
 

@@ -10,7 +10,8 @@ using namespace zkp;
 
 extern "C" {
 
-// op: 0 add, 1 sub, 2 mul (portable), 3 mul (carry-chain algorithm), 4 inv, 5 to_mont, 6 from_mont, 7 mul (64-bit host CIOS)
+// op: 0 add, 1 sub, 2 mul (portable), 3 mul (carry-chain algorithm), 4 inv, 5 to_mont, 6 from_mont, 7 mul (64-bit host CIOS),
+//     8 sqr (dedicated carry-chain squaring)
 int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   Fr x, y, r;
   memcpy(x.v, a, 32);
@@ -24,6 +25,7 @@ int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 5: r = fp_to_mont(x); break;
     case 6: r = fp_from_mont(x); break;
     case 7: r = fp_mul_host64(x, y); break;
+    case 8: r = fp_sqr_chain(x); break;
     default: return 1;
   }
   memcpy(out, r.v, 32);
@@ -43,6 +45,7 @@ int zkp_t_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 5: r = fp_to_mont(x); break;
     case 6: r = fp_from_mont(x); break;
     case 7: r = fp_mul_host64(x, y); break;
+    case 8: r = fp_sqr_chain(x); break;
     default: return 1;
   }
   memcpy(out, r.v, 48);

@@ -279,13 +279,17 @@ static size_t aff_next_bound(size_t m, size_t nb) { return (m + (m < nb ? m : nb
 
 // Measured on B200 (profiles/r02_msm_affine_ab.txt): a round costs ~0.28 ns per addition against 0.36 ns in XYZZ plus
 // ~1 ms of fixed latency (scan, inversion tree, one Fermat inversion), so rounds pay while they still hold tens of
-// millions of additions: 3 rounds at mean loads of 64..128 points per bucket (2^22..2^26 points); below 2^25 pairs
+// millions of additions: 2-4 rounds at mean loads of 64..128 points per bucket (2^22..2^26 points); below 2^25 pairs
 // the pipeline stays XYZZ-only (a 2^20 MSM is 8.4 ms without and 10.8 ms with rounds).
 uint32_t msm_affine_choose_rounds(size_t total, size_t total_buckets) {
   if (total < ((size_t)1 << 25) || total_buckets == 0) return 0;
   uint32_t lg = 0;
   for (size_t mean = total / total_buckets; mean > 1; mean >>= 1) lg++;
-  return lg > 3 ? (lg - 3 > 4 ? 4 : lg - 3) : 0;
+  // the fixed cost of a round weighs more on smaller problems: 2^22 points (54 M pairs) is best with 2 rounds, 2^24 and 2^26
+  // (201 M / 738 M pairs) with 4
+  const uint32_t keep = total >= ((size_t)1 << 27) ? 2 : (total >= ((size_t)1 << 26) ? 3 : 4);
+  const uint32_t r = lg > keep ? lg - keep : 0;
+  return r > 4 ? 4 : r;
 }
 
 size_t msm_affine_bound(size_t total, size_t nb, uint32_t rounds) {
