@@ -59,6 +59,8 @@ size_t zkp_plonk_circuit_len(const zkp_plonk_circuit* c);
 
 /* Circuit::compile (circuit.rs:166-197): pad to a power of two, 12 interpolations (one batched iNTT). */
 int zkp_plonk_compile(zkp_ctx* ctx, const zkp_plonk_circuit* c, zkp_plonk_compiled** out);
+/* Teardown order: a compiled circuit owns device buffers allocated through `ctx`; free it BEFORE zkp_ctx_destroy(ctx)
+ * (freeing it afterwards would touch a destroyed context). */
 void zkp_plonk_compiled_free(zkp_plonk_compiled* cc);
 size_t zkp_plonk_compiled_size(const zkp_plonk_compiled* cc);
 /* Coefficients of one compiled polynomial, zero-padded to `size` (which: 0..8 = f_a f_b f_c q_l q_r q_o q_m q_c pi,

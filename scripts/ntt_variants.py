@@ -3,20 +3,19 @@ The variant libraries are built HERE (nvcc cross-compiles) before the gpurun cal
 import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-K2 = ["-DNTT_KMAX=2", "-DNTT_TILE_LOG=10"]
 VARIANTS = {
-    "k2_th128_b6_pre1": K2 + ["-DNTT_MIN_BLOCKS=6", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
-    "k2_th128_b6_pre0": K2 + ["-DNTT_MIN_BLOCKS=6", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=0"],
-    "k2_th256_b3_pre1": K2 + ["-DNTT_MIN_BLOCKS=3", "-DNTT_THREADS_PER_CTA=256", "-DNTT_TW_PRELOAD=1"],
-    "k2_th128_b5_pre1": K2 + ["-DNTT_MIN_BLOCKS=5", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
-    "k3_t11_th256_b2_pre1": ["-DNTT_TW_PRELOAD=1"],
-    "k3_t10_th128_b4_pre1": ["-DNTT_TILE_LOG=10", "-DNTT_MIN_BLOCKS=4", "-DNTT_THREADS_PER_CTA=128", "-DNTT_TW_PRELOAD=1"],
+    "base": [],
+    "k1_b7": ["-DNTT_KMAX=1", "-DNTT_MIN_BLOCKS=7"],
+    "k1_b6": ["-DNTT_KMAX=1", "-DNTT_MIN_BLOCKS=6"],
+    "k2_b6": ["-DNTT_MIN_BLOCKS=6"],
+    "k2_th256_b3_t11": ["-DNTT_TILE_LOG=11", "-DNTT_THREADS_PER_CTA=256", "-DNTT_MIN_BLOCKS=2"],
+    "k2_th64_b10": ["-DNTT_THREADS_PER_CTA=64", "-DNTT_MIN_BLOCKS=10"],
 }
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "zkp-implementation_b200", "build.py"))
     b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
     for name, flags in VARIANTS.items():
-        print(name, b.build_cuda(force=True, extra_flags=flags, out_name="libzkp_var_%s.so" % name))
+        print(name, b.build_cuda(force=True, extra_flags=flags, out_name="libzkp_var_%s.so" % name, only=["ntt.cu"]))
     sys.exit(0)
 import numpy as np, torch
 import zkp_implementation_b200 as z

@@ -177,6 +177,7 @@ int zkp_ctx_synchronize(zkp_ctx* h) {
 
 int zkp_ctx_set_msm_window(zkp_ctx* h, uint32_t bits) {
   if (!h || (bits != 0 && (bits < 2 || bits > 22))) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);
   h->c.msm_window_bits = bits;
   return ZKP_OK;
 }
@@ -190,6 +191,7 @@ int zkp_ctx_set_msm_affine(zkp_ctx* h, int rounds) {
 
 int zkp_ctx_set_profiling(zkp_ctx* h, int on) {
   if (!h) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);
   h->c.profiling = on != 0;
   return ZKP_OK;
 }
@@ -634,12 +636,14 @@ int zkp_ntt_dist_permute_dev(zkp_ctx* h, const void* in_dev, void* out_dev, uint
 
 int zkp_dev_alloc(zkp_ctx* h, size_t bytes, void** out_dev) {
   if (!h || !out_dev) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);  // reads the context's stream / device: serialised with zkp_ctx_set_stream
   ZKP_TRY(rt::set_device(h->c.device));
   return rt::dev_malloc(out_dev, bytes);
 }
 
 int zkp_dev_free(zkp_ctx* h, void* dev) {
   if (!h) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);  // reads the context's stream / device: serialised with zkp_ctx_set_stream
   ZKP_TRY(rt::set_device(h->c.device));
   rt::sync(h->c.stream);
   rt::dev_free(dev);
@@ -648,6 +652,7 @@ int zkp_dev_free(zkp_ctx* h, void* dev) {
 
 int zkp_dev_copy(zkp_ctx* h, void* dst_dev, const void* src_dev, size_t bytes) {
   if (!h || (bytes && (!dst_dev || !src_dev))) return ZKP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->c.mu);  // reads the context's stream / device: serialised with zkp_ctx_set_stream
   ZKP_TRY(rt::set_device(h->c.device));
   return rt::d2d(dst_dev, src_dev, bytes, h->c.stream);
 }

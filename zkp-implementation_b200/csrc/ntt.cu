@@ -285,6 +285,12 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
   g.colbase = cb << q;
   g.w = a.w;
   uint32_t l0 = 0;
+#if NTT_KMAX == 1  // experiment knob: radix-2 steps only
+  while (l0 < r) {
+    tile_step<1>(lo, hi, g, l0, tid, nthreads);
+    l0 += 1;
+  }
+#else
   while (r - l0 >= 3) {
 #if NTT_KMAX >= 3
     tile_step<3>(lo, hi, g, l0, tid, nthreads);
@@ -299,6 +305,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
   } else if (r - l0 == 1) {
     tile_step<1>(lo, hi, g, l0, tid, nthreads);
   }
+#endif
   __syncthreads();
 
   // ---- store: un-bit-reverse the digit, apply inter-pass twiddle / coset / N^-1 ----
