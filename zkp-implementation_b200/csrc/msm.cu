@@ -45,6 +45,9 @@ static constexpr uint32_t RED_THREADS = 32;   // emulated build: one OS thread p
 #else
 static constexpr uint32_t RED_THREADS = 128;
 #endif
+#ifndef ZKP_RED_MIN_BLOCKS
+#define ZKP_RED_MIN_BLOCKS 1
+#endif
 static constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmTask {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTa
 static constexpr uint32_t MAX_RED_LEVELS = 26;
 
 // X^0[gb] = sum of the bucket's partial sums (tasks of a split bucket; heavily split ones were folded first)
-__global__ void __launch_bounds__(RED_THREADS) msm_bucket_gather_kernel(const G1Xyzz* __restrict__ partials,
+__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_bucket_gather_kernel(const G1Xyzz* __restrict__ partials,
                                                                         const uint32_t* __restrict__ task_off,
                                                                         const uint32_t* __restrict__ nfold,
                                                                         uint32_t total_buckets, G1Xyzz* __restrict__ x0) {
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(RED_THREADS) msm_bucket_gather_kernel(const G1
 }
 
 // out[i] = in[2i] + in[2i+1] over the concatenated sets (every set has an even number of entries)
-__global__ void __launch_bounds__(RED_THREADS) msm_pair_add_kernel(const G1Xyzz* __restrict__ in, uint32_t pairs,
+__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_pair_add_kernel(const G1Xyzz* __restrict__ in, uint32_t pairs,
                                                                    G1Xyzz* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pairs) return;
@@ -272,7 +275,7 @@ static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (lev
 // (large bucket sets), 2 when they are latency-bound (small ones)
 static constexpr uint32_t SUM_CHUNK_LARGE = 16 * RED_THREADS, SUM_CHUNK_SMALL = 2 * RED_THREADS;
 
-__global__ void __launch_bounds__(RED_THREADS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
+__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
                                                                     uint32_t nsets, uint32_t min_chunk,
                                                                     G1Xyzz* __restrict__ out) {
   __shared__ G1Xyzz sh[RED_THREADS];
