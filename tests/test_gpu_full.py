@@ -204,36 +204,34 @@ def test_msm_2p24_random_scalars_vs_oracle(zkp, gpu_engine, coracle):
     gpu_engine.srs_upload_dev(bases, 1)  # drop the table
 
 
-def test_affine_rounds_fall_back_when_memory_is_short(zkp, gpu_engine, coracle):
+def test_affine_rounds_fall_back_when_memory_is_short(zkp, coracle):
     """The round buffers of the batched-affine accumulation are all-or-nothing: with too little free HBM the MSM runs
-    XYZZ-only (rounds = 0) and returns the same point."""
+    XYZZ-only (rounds = 0) and returns the same point.  A fresh context (its scratch buffers start empty)."""
     import torch
 
     F = zkp.fields
-    n = 1 << 21
+    eng = zkp.Engine(0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = 1 << 22
     bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
-    gpu_engine.generate_bases_dev(0x5151, n, bases)
-    s = F.random_fr_mont(0x5152, n)
+    eng.generate_bases_dev(0x5153, n, bases)
+    s = F.random_fr_mont(0x5154, n)
     sd = _dev(s)
     want = coracle.msm_pippenger(s, _host(bases, 12))
-    gpu_engine.set_msm_affine(3)
+    eng.set_msm_affine(3)
     hog = None
     try:
-        out, _ = gpu_engine.msm_dev(sd, bases, n)
-        assert gpu_engine.last_affine_rounds() == 3 and (out == want).all()
-        # release the engine's round buffers by asking for a larger problem first is not possible from here; instead leave
-        # less free memory than the guard's margin (6 GiB) and force MORE rounds' worth of buffers with a larger MSM
         torch.cuda.empty_cache()
         free, _total = torch.cuda.mem_get_info()
-        hog = torch.empty(max(free - (5 << 30), 0), dtype=torch.uint8, device="cuda")
-        n2 = 1 << 22
-        bases2 = torch.zeros(n2 * 12, dtype=torch.int64, device="cuda")
-        gpu_engine.generate_bases_dev(0x5153, n2, bases2)
-        s2 = F.random_fr_mont(0x5154, n2)
-        out2, _ = gpu_engine.msm_dev(_dev(s2), bases2, n2)
-        assert gpu_engine.last_affine_rounds() == 0
-        assert (out2 == coracle.msm_pippenger(s2, _host(bases2, 12))).all()
+        hog = torch.empty(max(free - (5 << 30), 0), dtype=torch.uint8, device="cuda")  # less than the guard's 6 GiB margin
+        out, _ = eng.msm_dev(sd, bases, n)
+        assert eng.last_affine_rounds() == 0 and (out == want).all()
+        del hog
+        hog = None
+        torch.cuda.empty_cache()
+        out, _ = eng.msm_dev(sd, bases, n)
+        assert eng.last_affine_rounds() == 3 and (out == want).all()
     finally:
         del hog
         torch.cuda.empty_cache()
-        gpu_engine.set_msm_affine(-1)
+        eng.close()
