@@ -23,7 +23,7 @@ if os.environ.get("ZKP_L2_FETCH"):
     print("granularity now", v.value)
 eng = z.Engine(0, lib_path=os.environ.get("ZKP_LIB"))
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
-eng.set_profiling(True)
+eng.set_profiling(os.environ.get("ZKP_PROFILING", "1") != "0")  # profiling on = per-phase events, affine rounds on ONE stream
 bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
 eng.generate_bases_dev(0xB200, n, bases)
 scalars = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device="cuda")
