@@ -26,3 +26,15 @@ s = F.random_fr_mont(5, 5003)
 print("msm", eng.msm(s)[1], "launches", eng.last_launches("msm"))
 a = eng.vec(F.random_fr_mont(6, 9000)); eng.fr_scan(a, "mul"); eng.fr_batch_inverse(a)
 print("sanitize target OK")
+# round 2: batched-affine rounds (forced), windowed and fixed-base, odd sizes; NTT with the per-level tables
+eng.set_msm_affine(3)
+s2 = F.random_fr_mont(7, 5003)
+pts = srs.g1_limbs()
+print("msm affine windowed", eng.msm(s2, pts)[1], "rounds", eng.last_affine_rounds())
+eng.srs_precompute(7)
+print("msm affine fixed", eng.msm(s2)[1], "rounds", eng.last_affine_rounds())
+eng.set_msm_affine(-1)
+d = F.random_fr_mont(8, 1 << 13)
+eng.ntt(d, 13)
+eng.ntt(d, 13, inverse=True, coset=7)
+print("sanitize target round-2 OK")
