@@ -190,6 +190,10 @@ def test_batched_affine_rounds(zkp, engine, coracle, pyref, rounds):
         for val in (1, 5, pyref.R - 1):
             sv = F.fr_to_mont_array([val] * n)
             assert (engine.msm(sv, b)[0] == coracle.msm_pippenger(sv, b)).all(), val
+        if rounds == 2:  # one bucket owns more than AFF_TB_SERIAL threads of the round: the block-filled start-bucket list
+            big = np.tile(b[20:120], (26, 1))
+            sv = F.fr_to_mont_array([3] * big.shape[0])
+            assert (engine.msm(sv, big)[0] == coracle.msm_pippenger(sv, big)).all()
         # the same point n times: doublings all the way down
         same = np.repeat(b[5:6], 333, axis=0)
         out, inf = engine.msm(F.fr_to_mont_array([9] * 333), same)

@@ -58,7 +58,7 @@ struct MsmScratch {
   DevBuf bucket_start, bucket_end, task_meta, partials, seg_out, win_out;
   DevBuf misc;
   // batched-affine tree rounds (msm_affine.cu): ping-pong point buffers, denominator prefixes, inversion tree, run offsets
-  DevBuf aff_a, aff_b, aff_pre, aff_inv, aff_off;
+  DevBuf aff_a, aff_b, aff_pre, aff_inv, aff_off, aff_tb;
 };
 
 struct Ctx {

@@ -827,7 +827,7 @@ void msm_destroy(Ctx* ctx) {
   ctx->sort_hist.release();
   DevBuf* all[] = {&m.scalars, &m.bases, &m.keys_a, &m.keys_b, &m.vals_a, &m.vals_b, &m.sort_tmp, &m.bucket_start,
                    &m.bucket_end, &m.task_meta, &m.partials, &m.seg_out, &m.win_out, &m.misc, &m.aff_a, &m.aff_b, &m.aff_pre,
-                   &m.aff_inv, &m.aff_off};
+                   &m.aff_inv, &m.aff_off, &m.aff_tb};
   for (DevBuf* b : all) b->release();
 }
 

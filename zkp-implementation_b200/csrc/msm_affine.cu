@@ -49,6 +49,7 @@ struct AffRound {
   Fq* pre;                  // [M_out] exclusive prefix products of the denominators (per thread)
   Fq* tot;                  // [ceil(M_out / K)] per-thread products
   uint32_t* stats;          // profiling: stats[0] = M_in, stats[1] = M_out (null when profiling is off)
+  const uint32_t* tb;       // [ceil(M_out / K)] bucket holding output t * K (aff_start_bucket_kernel): no search per thread
 };
 
 // len_out[b] = ceil(len_in[b] / 2); entry nb = 0 so that the exclusive scan leaves M_out there
@@ -67,20 +68,42 @@ __global__ void __launch_bounds__(256) aff_len0_kernel(const uint32_t* __restric
   len[b] = (b < nb) ? (bend[b] - bstart[b]) : 0u;
 }
 
-// largest b with off[b] <= o < off[b + 1]
-__device__ __forceinline__ uint32_t aff_locate(const uint32_t* __restrict__ off, uint32_t nb, uint32_t o) {
-  uint32_t lo = 0, hi = nb;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (off[mid] > o) hi = mid; else lo = mid + 1;
+// tb[t] = the bucket holding output t * K, for every thread t of A / C.  A binary search per thread costs ~21 dependent
+// L2 reads before the first useful load (a third of kernel A's per-thread latency); the inverse map is a scatter: bucket
+// b owns the threads ceil(off_out[b] / K) .. ceil(off_out[b + 1] / K) - 1 (3 on average).  A bucket owning more than
+// AFF_TB_SERIAL threads (skewed scalars: few, heavily loaded buckets) goes to a list filled by whole blocks.
+static constexpr uint32_t AFF_TB_SERIAL = 64;
+__global__ void __launch_bounds__(256) aff_start_bucket_kernel(const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                               uint32_t* __restrict__ tb, uint32_t* __restrict__ heavy,
+                                                               uint32_t heavy_cap) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const uint32_t ob = off_out[b], oe = off_out[b + 1];
+  if (oe == ob) return;
+  const uint32_t t0 = (ob + AFF_K - 1) / AFF_K, t1 = (oe + AFF_K - 1) / AFF_K;
+  if (t1 - t0 > AFF_TB_SERIAL) {
+    const uint32_t slot = atomicAdd(heavy, 1u);
+    if (slot < heavy_cap) { heavy[1 + slot] = b; return; }
   }
-  return lo - 1;
+  for (uint32_t t = t0; t < t1; t++) tb[t] = b;
+}
+
+__global__ void __launch_bounds__(256) aff_start_bucket_heavy_kernel(const uint32_t* __restrict__ off_out,
+                                                                     uint32_t* __restrict__ tb,
+                                                                     const uint32_t* __restrict__ heavy, uint32_t heavy_cap) {
+  uint32_t nh = heavy[0];
+  if (nh > heavy_cap) nh = heavy_cap;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    const uint32_t b = heavy[1 + h];
+    const uint32_t t0 = (off_out[b] + AFF_K - 1) / AFF_K, t1 = (off_out[b + 1] + AFF_K - 1) / AFF_K;
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) tb[t] = b;
+  }
 }
 
 // idx[k] = position of the first operand of output o0 + k in the input order, bit 31 set when the output is a lone
 // carried-over point; AFF_NONE past the end
-__device__ __forceinline__ void aff_walk(const AffRound& a, uint32_t o0, uint32_t mout, uint32_t (&idx)[AFF_K]) {
-  uint32_t b = aff_locate(a.off_out, a.nb, o0);
+__device__ __forceinline__ void aff_walk(const AffRound& a, uint32_t t, uint32_t o0, uint32_t mout, uint32_t (&idx)[AFF_K]) {
+  uint32_t b = a.tb[t];
   uint32_t ob = a.off_out[b], oe = a.off_out[b + 1], ib = a.off_in[b], ie = a.off_in[b + 1];
 #pragma unroll
   for (uint32_t k = 0; k < AFF_K; k++) {
@@ -149,7 +172,7 @@ __global__ void __launch_bounds__(AFF_THREADS) aff_denominators_kernel(AffRound 
   if (o0_64 >= mout) return;
   const uint32_t o0 = (uint32_t)o0_64;
   uint32_t idx[AFF_K], r1[AFF_K], r2[AFF_K];
-  aff_walk(a, o0, mout, idx);
+  aff_walk(a, t, o0, mout, idx);
   aff_refs<FIRST>(a, idx, r1, r2);
   Fq run = Fq::one();
   // the x coordinates of element k + 1 are requested before element k is multiplied in
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 3) aff_add_kernel(AffRound a) {
   if (o0_64 >= mout) return;
   const uint32_t o0 = (uint32_t)o0_64;
   uint32_t idx[AFF_K], r1[AFF_K], r2[AFF_K];
-  aff_walk(a, o0, mout, idx);
+  aff_walk(a, t, o0, mout, idx);
   aff_refs<FIRST>(a, idx, r1, r2);
   Fq inv = ld_fq(a.tot + t);  // 1 / (product of this thread's denominators)
   // the operands of element k - 1 are requested before element k is computed (same pattern as msm_accumulate_kernel)
@@ -339,6 +362,11 @@ int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, cons
   ZKP_TRY(m.aff_pre.reserve(m1 * sizeof(Fq)));
   ZKP_TRY(m.aff_inv.reserve(inv_elems * sizeof(Fq)));
   ZKP_TRY(m.aff_off.reserve(2 * ((size_t)nb + 1) * sizeof(uint32_t)));
+  // start-bucket table of the A / C threads + the list of buckets that own more than AFF_TB_SERIAL of them
+  const size_t heavy_cap = threads1 / AFF_TB_SERIAL + 1;
+  ZKP_TRY(m.aff_tb.reserve((threads1 + 1 + heavy_cap + 1) * sizeof(uint32_t)));
+  uint32_t* tb = m.aff_tb.as<uint32_t>();
+  uint32_t* tb_heavy = tb + threads1 + 1;
   uint32_t* off_cur = m.aff_off.as<uint32_t>();
   uint32_t* off_nxt = off_cur + (nb + 1);
   ZKP_LAUNCH_NOSYNC(aff_len0_kernel, dim3((nb + 256) / 256), dim3(256), 0, st, bstart, bend, nb, off_cur);
@@ -361,6 +389,12 @@ int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, cons
     a.out = out;
     a.pre = m.aff_pre.as<Fq>();
     a.stats = nullptr;
+    a.tb = tb;
+    ZKP_TRY(rt::dev_memset(tb_heavy, 0, sizeof(uint32_t), st));
+    ZKP_LAUNCH_NOSYNC(aff_start_bucket_kernel, dim3((nb + 255) / 256), dim3(256), 0, st, (const uint32_t*)off_nxt, nb, tb,
+                      tb_heavy, (uint32_t)heavy_cap);
+    ZKP_LAUNCH_NOSYNC(aff_start_bucket_heavy_kernel, dim3(256), dim3(256), 0, st, (const uint32_t*)off_nxt, tb,
+                      (const uint32_t*)tb_heavy, (uint32_t)heavy_cap);
 #ifndef ZKP_EMU
     if (ctx->profiling && r + 1 < (uint32_t)Ctx::AFF_STATS) {
       if (!ctx->aff_stats_dev) ZKP_TRY(rt::dev_malloc((void**)&ctx->aff_stats_dev, Ctx::AFF_STATS * sizeof(uint32_t)));
@@ -417,7 +451,7 @@ int msm_affine_rounds_dev(Ctx* ctx, uint32_t rounds, const uint32_t* svals, cons
     } else {
       ZKP_LAUNCH_NOSYNC(aff_add_kernel<false>, dim3(aff_blocks(nthreads)), dim3(AFF_THREADS), 0, st, a);
     }
-    ctx->msm_launches += 3 + 2 * (uint32_t)(nl - 1) + 1;
+    ctx->msm_launches += 5 + 2 * (uint32_t)(nl - 1) + 1;
     in = out;
     mcur = mout;
     uint32_t* t = off_cur; off_cur = off_nxt; off_nxt = t;
