@@ -47,6 +47,29 @@ def test_field_ops(hostlib, zkp, name):
     assert _unpack(out) == a
 
 
+def test_fq_inverse_by_division_steps(hostlib, zkp):
+    """csrc/inv_gcd.cuh (the inversion of the batched-affine MSM rounds): safegcd division steps against pow(a, -1, p)
+    and against the Fermat ladder it replaces -- small values, values next to p, every single-bit value (long runs of
+    even steps), all-ones patterns, 0 -> 0, and random residues."""
+    F = zkp.fields
+    fn, mod, n, R = hostlib.zkp_t_fq_op, F.FQ_MODULUS, 12, F.FQ_R
+    rnd = random.Random(7)
+    vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, R % mod, pow(R, -1, mod), (1 << 380), (1 << 380) - 1,
+            int("55" * 47, 16) % mod, int("aa" * 47, 16) % mod]
+    vals += [1 << k for k in range(381)] + [(mod - (1 << k)) % mod for k in range(381)]
+    vals += [rnd.randrange(1, mod) for _ in range(3000)]
+    out, out2 = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
+    for a in vals:  # `a` is the stored (Montgomery) residue: a = x R, expected x^-1 R = a^-1 R^2
+        assert fn(9, _pack(a, n), None, out) == 0
+        assert _unpack(out) == pow(a, -1, mod) * R * R % mod, hex(a)
+    for a in vals[:40]:
+        fn(4, _pack(a, n), None, out2)
+        fn(9, _pack(a, n), None, out)
+        assert _unpack(out) == _unpack(out2)
+    fn(9, _pack(0, n), None, out)
+    assert _unpack(out) == 0
+
+
 def test_group_law_corner_cases(hostlib, zkp, pyref):
     o = pyref
     P, R = o.P, o.FQ_MONT_R

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_affine.cu", "gen.cu", "poly.cu", "sort.cu"]
-HEADERS = ["field.cuh", "curve.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
+HEADERS = ["field.cuh", "curve.cuh", "inv_gcd.cuh", "memops.cuh", "engine.h", "runtime.h", "poly.h"]
 HOST_DIR = os.path.join(PKG, "host")
 HOST_SOURCES = ["plonk.cpp", "kzg.cpp", "transcript_api.cpp"]  # host orchestration above the C ABI (include/zkp_plonk.h), plain g++
 HOST_HEADERS = ["mont_host.hpp", "transcript.hpp"]
@@ -95,7 +95,7 @@ def build_cuda(force: bool = False, extra_flags: list[str] | None = None, out_na
 
 def build_hosttest(force: bool = False) -> str:
     out = os.path.join(PKG, "libzkp_hosttest.so")
-    deps = [os.path.join(CSRC, f) for f in ("host_testapi.cpp", "field.cuh", "curve.cuh")]
+    deps = [os.path.join(CSRC, f) for f in ("host_testapi.cpp", "field.cuh", "curve.cuh", "inv_gcd.cuh")]
     if not force and _newer(out, deps):
         return out
     _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + CSRC, os.path.join(CSRC, "host_testapi.cpp"), "-o", out])

@@ -47,7 +47,7 @@ static void write_affine_batch(const G1Xyzz* p, uint32_t count, uint64_t* out_xy
     pre[i] = prod;
     if (!p[i].is_inf()) prod = prod * (p[i].zz * p[i].zzz);
   }
-  Fq inv = fp_inv(prod);
+  Fq inv = fq_inv_gcd(prod);
   for (uint32_t i = count; i-- > 0;) {
     G1Affine a = G1Affine::infinity();
     if (!p[i].is_inf()) {

@@ -9,6 +9,7 @@
 // (0, 0) is not on y^2 = x^3 + 4 and serves as the point at infinity (ark's `infinity: bool`).
 #pragma once
 #include "field.cuh"
+#include "inv_gcd.cuh"
 
 namespace zkp {
 
@@ -123,7 +124,7 @@ ZKP_HD_NOINLINE G1Affine xyzz_to_affine(const G1Xyzz& p) {
   if (p.is_inf()) return G1Affine::infinity();
   // 1/ZZZ, then 1/ZZ = ZZZ^-2 * ZZ^2 ... cheaper: one inversion of ZZ*ZZZ
   Fq t = p.zz * p.zzz;
-  Fq ti = fp_inv(t);
+  Fq ti = fq_inv_gcd(t);
   Fq zz_inv = ti * p.zzz;
   Fq zzz_inv = ti * p.zz;
   G1Affine r;

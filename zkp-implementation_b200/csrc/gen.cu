@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(GEN_THREADS) batch_normalise_kernel(const G1Xy
     st_fq(&out[first + i].x, prod);
     if (!p.is_inf()) prod = prod * (p.zz * p.zzz);
   }
-  Fq inv = fp_inv(prod);
+  Fq inv = fq_inv_gcd(prod);
   for (int i = (int)cnt - 1; i >= 0; i--) {
     const G1Xyzz p = ld_xyzz(tmp + first + i);
     G1Affine a = G1Affine::infinity();

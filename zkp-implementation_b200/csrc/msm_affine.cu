@@ -24,6 +24,7 @@
 // P + O, O + P, P + P (tangent slope 3x^2 / 2y), P + (-P) = O.  Field arithmetic is exact: the round's output points
 // are the unique affine representatives, whatever K or R.
 #include "engine.h"
+#include "inv_gcd.cuh"
 #include "memops.cuh"
 
 namespace zkp {
@@ -163,8 +164,14 @@ __device__ __forceinline__ Fq aff_ld_ref_x(const AffRound& a, uint32_t ref) {
 }
 
 // ---- A: denominators ------------------------------------------------------------------------------
+#ifndef ZKP_AFF_A_BLOCKS
+#define ZKP_AFF_A_BLOCKS 4
+#endif
+#ifndef ZKP_AFF_A_PREFETCH
+#define ZKP_AFF_A_PREFETCH 1
+#endif
 template <bool FIRST>
-__global__ void __launch_bounds__(AFF_THREADS) aff_denominators_kernel(AffRound a) {
+__global__ void __launch_bounds__(AFF_THREADS, ZKP_AFF_A_BLOCKS) aff_denominators_kernel(AffRound a) {
   const uint32_t mout = a.off_out[a.nb];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t o0_64 = (uint64_t)t * AFF_K;
@@ -176,14 +183,20 @@ __global__ void __launch_bounds__(AFF_THREADS) aff_denominators_kernel(AffRound 
   aff_refs<FIRST>(a, idx, r1, r2);
   Fq run = Fq::one();
   // the x coordinates of element k + 1 are requested before element k is multiplied in
+#if ZKP_AFF_A_PREFETCH
   Fq nx1 = aff_ld_ref_x<FIRST>(a, r1[0]), nx2 = aff_ld_ref_x<FIRST>(a, r2[0]);
+#endif
 #pragma unroll 1
   for (uint32_t k = 0; k < AFF_K; k++) {
+#if ZKP_AFF_A_PREFETCH
     const Fq x1 = nx1, x2 = nx2;
     if (k + 1 < AFF_K) {
       nx1 = aff_ld_ref_x<FIRST>(a, r1[k + 1]);
       nx2 = aff_ld_ref_x<FIRST>(a, r2[k + 1]);
     }
+#else
+    const Fq x1 = aff_ld_ref_x<FIRST>(a, r1[k]), x2 = aff_ld_ref_x<FIRST>(a, r2[k]);
+#endif
     const uint32_t id = idx[k];
     if (id == AFF_NONE || (id & AFF_SIGN)) continue;  // nothing / a carried-over point: no denominator
     Fq den = fp_sub(x2, x1);
@@ -200,8 +213,14 @@ __global__ void __launch_bounds__(AFF_THREADS) aff_denominators_kernel(AffRound 
 }
 
 // ---- C: additions ----------------------------------------------------------------------------------
+#ifndef ZKP_AFF_C_BLOCKS
+#define ZKP_AFF_C_BLOCKS 4
+#endif
+#ifndef ZKP_AFF_C_PREFETCH
+#define ZKP_AFF_C_PREFETCH 0
+#endif
 template <bool FIRST>
-__global__ void __launch_bounds__(AFF_THREADS, 3) aff_add_kernel(AffRound a) {
+__global__ void __launch_bounds__(AFF_THREADS, ZKP_AFF_C_BLOCKS) aff_add_kernel(AffRound a) {
   const uint32_t mout = a.off_out[a.nb];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t o0_64 = (uint64_t)t * AFF_K;
@@ -212,14 +231,20 @@ __global__ void __launch_bounds__(AFF_THREADS, 3) aff_add_kernel(AffRound a) {
   aff_refs<FIRST>(a, idx, r1, r2);
   Fq inv = ld_fq(a.tot + t);  // 1 / (product of this thread's denominators)
   // the operands of element k - 1 are requested before element k is computed (same pattern as msm_accumulate_kernel)
+#if ZKP_AFF_C_PREFETCH
   G1Affine n1 = aff_ld_ref<FIRST>(a, r1[AFF_K - 1]), n2 = aff_ld_ref<FIRST>(a, r2[AFF_K - 1]);
+#endif
 #pragma unroll 1
   for (int k = AFF_K - 1; k >= 0; k--) {
+#if ZKP_AFF_C_PREFETCH
     const G1Affine p1 = n1, p2 = n2;
     if (k > 0) {
       n1 = aff_ld_ref<FIRST>(a, r1[k - 1]);
       n2 = aff_ld_ref<FIRST>(a, r2[k - 1]);
     }
+#else
+    const G1Affine p1 = aff_ld_ref<FIRST>(a, r1[k]), p2 = aff_ld_ref<FIRST>(a, r2[k]);
+#endif
     const uint32_t id = idx[k];
     if (id == AFF_NONE) continue;
     G1Affine* dst = a.out + o0 + k;
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(AFF_THREADS) aff_inv_direct_kernel(Fq* __restr
   const uint32_t n = aff_level_count(mout_ptr, div);
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n) return;
-  st_fq(v + u, fp_inv(ld_fq(v + u)));  // products of non-zero denominators: never zero
+  st_fq(v + u, fq_inv_gcd(ld_fq(v + u)));  // products of non-zero denominators: never zero
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,19 +325,20 @@ __global__ void __launch_bounds__(AFF_THREADS) aff_inv_direct_kernel(Fq* __restr
 // Upper bound of the number of points after one more round: sum_b ceil(L_b / 2) <= (M + #non-empty runs) / 2
 static size_t aff_next_bound(size_t m, size_t nb) { return (m + (m < nb ? m : nb) + 1) / 2; }
 
-// Measured on B200 (profiles/r02_msm_affine_ab.txt): a round costs ~0.28 ns per addition against 0.36 ns in XYZZ plus
-// ~1 ms of fixed latency (scan, inversion tree, one Fermat inversion), so rounds pay while they still hold tens of
-// millions of additions: 2-4 rounds at mean loads of 64..128 points per bucket (2^22..2^26 points); below 2^25 pairs
-// the pipeline stays XYZZ-only (a 2^20 MSM is 8.4 ms without and 10.8 ms with rounds).
+// Measured on B200 (profiles/r02_msm_affine_ab.txt): a round costs ~0.22 ns per addition against 0.36 ns in XYZZ plus
+// ~0.35 ms of fixed latency (scans, inversion tree, one division-step inversion -- 0.9 ms while that inversion was a
+// Fermat ladder), and round j holds total / 2^j additions: it pays while that is >= ~3 M.  2^20 points (13.6 M pairs):
+// 2 rounds, 2^22: 3-4, 2^24: 5; never more rounds than the mean run is deep.
+#ifndef ZKP_AFF_MAX_ROUNDS
+#define ZKP_AFF_MAX_ROUNDS 5
+#endif
 uint32_t msm_affine_choose_rounds(size_t total, size_t total_buckets) {
-  if (total < ((size_t)1 << 25) || total_buckets == 0) return 0;
+  if (total_buckets == 0) return 0;
   uint32_t lg = 0;
   for (size_t mean = total / total_buckets; mean > 1; mean >>= 1) lg++;
-  // the fixed cost of a round weighs more on smaller problems: 2^22 points (54 M pairs) is best with 2 rounds, 2^24 and 2^26
-  // (201 M / 738 M pairs) with 4
-  const uint32_t keep = total >= ((size_t)1 << 27) ? 2 : (total >= ((size_t)1 << 26) ? 3 : 4);
-  const uint32_t r = lg > keep ? lg - keep : 0;
-  return r > 4 ? 4 : r;
+  uint32_t r = 0;
+  while (r < ZKP_AFF_MAX_ROUNDS && r < lg && (total >> (r + 1)) >= ((size_t)3 << 20)) r++;
+  return r;
 }
 
 size_t msm_affine_bound(size_t total, size_t nb, uint32_t rounds) {
