@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import zkp_implementation_b200 as z
 SECRET = 0x1F2E3D4C5B6A79881234567
 BLIND = [(0xABCDEF0123456789 * (i + 3) ** 7) % z.FR_MODULUS for i in range(9)]
-eng = z.Engine(0)
+eng = z.Engine(0, lib_path=os.environ.get("ZKP_LIB"))
 for k in [int(a) for a in sys.argv[1:]] or [16, 20]:
     n = 1 << k
     eng.srs_generate(SECRET, n + 3, want_points=False)

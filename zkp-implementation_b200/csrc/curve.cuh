@@ -33,13 +33,13 @@ struct alignas(16) G1Xyzz {
 ZKP_HD G1Xyzz xyzz_dbl(const G1Xyzz& p) {
   if (p.is_inf()) return p;
   Fq u = fp_dbl(p.y);
-  Fq v = fp_sqr(u);
+  Fq v = fq_sqr(u);
   Fq w = u * v;
   Fq s = p.x * v;
-  Fq xx = fp_sqr(p.x);
+  Fq xx = fq_sqr(p.x);
   Fq m = fp_add(fp_dbl(xx), xx);
   G1Xyzz r;
-  r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+  r.x = fp_sub(fq_sqr(m), fp_dbl(s));
   r.y = fp_sub(m * fp_sub(s, r.x), w * p.y);
   r.zz = v * p.zz;
   r.zzz = w * p.zzz;
@@ -49,13 +49,13 @@ ZKP_HD G1Xyzz xyzz_dbl(const G1Xyzz& p) {
 // Doubling of an affine point (ZZ = ZZZ = 1): mdbl-2008-s-1
 ZKP_HD G1Xyzz xyzz_dbl_affine(const G1Affine& p) {
   Fq u = fp_dbl(p.y);
-  Fq v = fp_sqr(u);
+  Fq v = fq_sqr(u);
   Fq w = u * v;
   Fq s = p.x * v;
-  Fq xx = fp_sqr(p.x);
+  Fq xx = fq_sqr(p.x);
   Fq m = fp_add(fp_dbl(xx), xx);
   G1Xyzz r;
-  r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+  r.x = fp_sub(fq_sqr(m), fp_dbl(s));
   r.y = fp_sub(m * fp_sub(s, r.x), w * p.y);
   r.zz = v;
   r.zzz = w;
@@ -75,10 +75,10 @@ ZKP_HD void xyzz_madd(G1Xyzz& acc, const G1Affine& q) {
     if (r.is_zero()) { acc = xyzz_dbl_affine(q); } else { acc = G1Xyzz::infinity(); }
     return;
   }
-  Fq pp = fp_sqr(p);
+  Fq pp = fq_sqr(p);
   Fq ppp = p * pp;
   Fq qq = acc.x * pp;
-  Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
+  Fq x3 = fp_sub(fp_sub(fq_sqr(r), ppp), fp_dbl(qq));
   Fq y3 = fp_sub(r * fp_sub(qq, x3), acc.y * ppp);
   acc.x = x3;
   acc.y = y3;
@@ -100,10 +100,10 @@ ZKP_HD void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
     if (r.is_zero()) { a = xyzz_dbl(a); } else { a = G1Xyzz::infinity(); }
     return;
   }
-  Fq pp = fp_sqr(p);
+  Fq pp = fq_sqr(p);
   Fq ppp = p * pp;
   Fq qq = u1 * pp;
-  Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
+  Fq x3 = fp_sub(fp_sub(fq_sqr(r), ppp), fp_dbl(qq));
   Fq y3 = fp_sub(r * fp_sub(qq, x3), s1 * ppp);
   a.x = x3;
   a.y = y3;

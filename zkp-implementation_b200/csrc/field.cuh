@@ -619,6 +619,18 @@ ZKP_HD Fr operator-(const Fr& a, const Fr& b) { return fp_sub(a, b); }
 ZKP_HD Fr operator*(const Fr& a, const Fr& b) { return fp_mul(a, b); }
 ZKP_HD Fq operator+(const Fq& a, const Fq& b) { return fp_add(a, b); }
 ZKP_HD Fq operator-(const Fq& a, const Fq& b) { return fp_sub(a, b); }
+// -DZKP_FQ_CALL (per translation unit): Fq products of the curve formulas become calls of ONE out-of-line multiplier /
+// squarer instead of ~4.5 KB of inlined SASS each.  A point addition is then ~1 KB of code around a 10 KB callee that
+// stays in the instruction cache, instead of 50-100 KB of straight-line code that a small, latency-bound launch fetches
+// cold (the reduction levels and short accumulations of 2^16..2^20-point MSMs).  Arguments travel in registers.
+#if defined(ZKP_FQ_CALL) && ZKP_PTX_DEVICE && defined(__CUDACC__)
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return fp_mul(a, b); }
+static __device__ __noinline__ Fq fq_sqr_call(Fq a) { return fp_sqr(a); }
+ZKP_HD Fq operator*(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+ZKP_HD Fq fq_sqr(const Fq& a) { return fq_sqr_call(a); }
+#else
 ZKP_HD Fq operator*(const Fq& a, const Fq& b) { return fp_mul(a, b); }
+ZKP_HD Fq fq_sqr(const Fq& a) { return fp_sqr(a); }
+#endif
 
 }  // namespace zkp

@@ -16,8 +16,9 @@
 //   5. accumulate  one thread per task: XYZZ accumulator += affine base (mixed add, 8M+2S),
 //                  next base prefetched while the current add runs
 //   6. reduce      sum_b (b+1) B_b per bucket set by bit planes of the bucket index: level l halves the array
-//                  (one independent addition per thread) and A_l = sum of the odd entries of level l, so the
-//                  serial depth is c - 1 additions however many buckets there are
+//                  (one independent addition per thread) and A_l = sum of the odd entries of level l, summed by
+//                  pairwise trees that advance in the same steps, so the serial depth is c - 1 additions + the
+//                  combine however many buckets there are
 //   7. host        windowed mode only: Horner over the W window sums; the caller normalises (one inversion)
 //
 // Two modes.  WINDOWED (ad-hoc bases): window w has its own 2^(c-1) buckets.  FIXED-BASE (the resident SRS
@@ -25,6 +26,12 @@
 // table entry (w, i) and ALL windows share one bucket set -- W times fewer buckets to reduce, no Horner, and
 // the cheaper reduction lets c grow by a few bits (fewer windows, fewer additions).
 #include <string.h>
+
+// This translation unit's Fq products are calls of one out-of-line multiplier (field.cuh): its kernels that matter for
+// small MSMs are short launches whose straight-line code was fetched cold (2^16: 1.69 -> 1.44 ms; 2^20 / 2^24 unchanged).
+#ifndef ZKP_FQ_INLINE
+#define ZKP_FQ_CALL 1
+#endif
 
 #include "engine.h"
 #include "memops.cuh"
@@ -254,134 +261,110 @@ __global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_bucket_ga
   st_xyzz(x0 + gb, acc);
 }
 
-// out[i] = in[2i] + in[2i+1] over the concatenated sets (every set has an even number of entries)
-__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_pair_add_kernel(const G1Xyzz* __restrict__ in, uint32_t pairs,
-                                                                   G1Xyzz* __restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pairs) return;
-  G1Xyzz a = ld_xyzz(in + 2 * (size_t)i);
-  const G1Xyzz b = ld_xyzz(in + 2 * (size_t)i + 1);
-  xyzz_add(a, b);
-  st_xyzz(out + i, a);
-}
-
-// A_l partial sums: block (bx, y = l * nsets + w) sums a chunk of the odd entries of X^l of set w
-struct RedLevels {
-  uint32_t off[MAX_RED_LEVELS + 1];  // element offset of X^l (layout [set][m_l]); off[levels] = X^levels (one entry per set)
-  uint32_t m[MAX_RED_LEVELS + 1];    // entries per set at level l
+// The tree.  Step L (L = 0 .. levels - 1) holds (L + 1) * (m >> (L + 1)) independent additions per set, all ONE addition deep:
+//   main     X^(L+1)[j] = X^L[2j] + X^L[2j+1]
+//   plane p  (p < L) P_p^(L+1)[j] = P_p^L[2j] + P_p^L[2j+1], where P_p^(p+1)[j] = X^p[2j+1] is read in place -- the pairwise
+//            tree over the odd entries of X^p, one level per step in lockstep with the main tree.
+// After the last step X^levels[0] = G and P_p^levels[0] = A_p (A_(levels-1) = X^(levels-1)[1] is never added to anything),
+// so the serial depth of the whole reduction is `levels` additions + the combine, 2m additions in all (as before: the
+// plane sums used to be separate chunked sums + a second stage + a combine launch, ~3x the depth).
+// Wide steps are one launch each; once a step has <= TAIL_ITEMS additions per set the rest runs in ONE launch, one block
+// per set with a block barrier per step, and the same block finishes F = G + sum_l 2^l A_l (thread l doubles A_l l times,
+// then a tree over the planes).
+struct RedTree {
+  uint32_t off[MAX_RED_LEVELS + 1];   // element offset of X^l, layout [set][m >> l]; off[levels] = X^levels (one entry per set)
+  uint32_t poff[MAX_RED_LEVELS + 1];  // plane p's ping-pong buffer, layout [2][set][h_p], h_p = max(m >> (p + 2), 1)
+  uint32_t m, levels, nsets;
 };
-static constexpr uint32_t SUM_CHUNKS = 512;           // stage-1 blocks per (level, set) for the largest level
-// entries per stage-1 block: 16 serial additions per thread ahead of the 7-step tree when the sums are throughput-bound
-// (large bucket sets), 2 when they are latency-bound (small ones)
-static constexpr uint32_t SUM_CHUNK_LARGE = 16 * RED_THREADS, SUM_CHUNK_SMALL = 2 * RED_THREADS;
+#ifdef ZKP_EMU
+static constexpr uint32_t TAIL_THREADS = 32;
+#else
+static constexpr uint32_t TAIL_THREADS = 256;
+#endif
+static constexpr uint32_t TAIL_ITEMS = 2 * TAIL_THREADS;
 
-__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_plane_sum_kernel(const G1Xyzz* __restrict__ buf, RedLevels lv,
-                                                                    uint32_t nsets, uint32_t min_chunk,
-                                                                    G1Xyzz* __restrict__ out) {
-  __shared__ G1Xyzz sh[RED_THREADS];
-  const uint32_t l = blockIdx.y / nsets, w = blockIdx.y - l * nsets, tid = threadIdx.x;
-  const uint32_t count = lv.m[l] >> 1;  // odd entries
-  uint32_t chunk = (count + gridDim.x - 1) / gridDim.x;
-  if (chunk < min_chunk) chunk = min_chunk;  // short arrays: fewer, fuller blocks
-  const uint32_t lo = blockIdx.x * chunk;
-  if (lo >= count) {  // block-uniform: nothing to sum
-    if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, G1Xyzz::infinity());
-    return;
-  }
-  const uint32_t hi = (lo + chunk < count) ? lo + chunk : count;
-  const G1Xyzz* in = buf + lv.off[l] + (size_t)w * lv.m[l];
-  G1Xyzz acc = G1Xyzz::infinity();
-  for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
-    G1Xyzz p = ld_xyzz(in + 2 * (size_t)i + 1);
-    xyzz_add(acc, p);
-  }
-  st_xyzz(&sh[tid], acc);
-  __syncthreads();
-  for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
-      xyzz_add(a, b);
-      st_xyzz(&sh[tid], a);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) st_xyzz(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz(&sh[0]));
+__device__ __forceinline__ uint32_t tree_plane_len(const RedTree& t, uint32_t p) {
+  const uint32_t h = t.m >> (p + 2);
+  return h ? h : 1u;
 }
 
-// The last levels (<= TAIL_M entries per set) in ONE launch: block w walks set w's remaining levels, one
-// __syncthreads between levels instead of one launch per level (a level is a single addition deep).
-static constexpr uint32_t TAIL_M = 8 * RED_THREADS;
-
-__global__ void __launch_bounds__(RED_THREADS) msm_pair_tail_kernel(G1Xyzz* __restrict__ buf, RedLevels lv, uint32_t l0,
-                                                                    uint32_t levels) {
-  const uint32_t w = blockIdx.x, tid = threadIdx.x;
-  for (uint32_t l = l0; l < levels; l++) {
-    const uint32_t m = lv.m[l];
-    const G1Xyzz* in = buf + lv.off[l] + (size_t)w * m;
-    G1Xyzz* out = buf + lv.off[l + 1] + (size_t)w * (m >> 1);
-    for (uint32_t i = tid; i < (m >> 1); i += blockDim.x) {
-      G1Xyzz a = ld_xyzz(in + 2 * (size_t)i);
-      const G1Xyzz b = ld_xyzz(in + 2 * (size_t)i + 1);
-      xyzz_add(a, b);
-      st_xyzz(out + i, a);
+// item (p, j) of set w at step L: p == L is the main tree, p < L plane p
+__device__ __forceinline__ void tree_item(G1Xyzz* __restrict__ buf, const RedTree& t, uint32_t L, uint32_t w, uint32_t p,
+                                          uint32_t j) {
+  const G1Xyzz *a, *b;
+  G1Xyzz* dst;
+  if (p == L) {
+    const G1Xyzz* in = buf + t.off[L] + (size_t)w * (t.m >> L);
+    a = in + 2 * (size_t)j;
+    b = a + 1;
+    dst = buf + t.off[L + 1] + (size_t)w * (t.m >> (L + 1)) + j;
+  } else {
+    const uint32_t hp = tree_plane_len(t, p);
+    G1Xyzz* pb = buf + t.poff[p];
+    const uint32_t oh = (L - p - 1) & 1u;
+    dst = pb + ((size_t)oh * t.nsets + w) * hp + j;
+    if (L == p + 1) {
+      const G1Xyzz* in = buf + t.off[p] + (size_t)w * (t.m >> p);
+      a = in + 4 * (size_t)j + 1;
+      b = a + 2;
+    } else {
+      const G1Xyzz* in = pb + ((size_t)(oh ^ 1u) * t.nsets + w) * hp;
+      a = in + 2 * (size_t)j;
+      b = a + 1;
     }
-    __syncthreads();
   }
+  G1Xyzz x = ld_xyzz(a);
+  const G1Xyzz y = ld_xyzz(b);
+  xyzz_add(x, y);
+  st_xyzz(dst, x);
 }
 
-// stage 2: A[y] = sum of the stage-1 partials of (level, set) y (layout [y][chunks])
-__global__ void __launch_bounds__(RED_THREADS) msm_plane_sum2_kernel(const G1Xyzz* __restrict__ part, uint32_t chunks,
+__global__ void __launch_bounds__(RED_THREADS, ZKP_RED_MIN_BLOCKS) msm_tree_step_kernel(G1Xyzz* __restrict__ buf, RedTree t,
+                                                                                       uint32_t L) {
+  const uint32_t half_log = t.levels - L - 1;
+  const uint32_t per_set = (L + 1) << half_log;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)per_set * t.nsets) return;
+  const uint32_t w = (uint32_t)(idx / per_set);
+  const uint32_t rem = (uint32_t)(idx - (uint64_t)w * per_set);
+  tree_item(buf, t, L, w, rem >> half_log, rem & ((1u << half_log) - 1));
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) msm_tree_tail_kernel(G1Xyzz* __restrict__ buf, RedTree t, uint32_t L0,
                                                                      G1Xyzz* __restrict__ out) {
-  __shared__ G1Xyzz sh[RED_THREADS];
-  const uint32_t tid = threadIdx.x;
-  const G1Xyzz* in = part + (size_t)blockIdx.x * chunks;
-  G1Xyzz acc = G1Xyzz::infinity();
-  for (uint32_t i = tid; i < chunks; i += blockDim.x) {
-    G1Xyzz p = ld_xyzz(in + i);
-    xyzz_add(acc, p);
-  }
-  st_xyzz(&sh[tid], acc);
-  __syncthreads();
-  for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
-      xyzz_add(a, b);
-      st_xyzz(&sh[tid], a);
-    }
+  __shared__ G1Xyzz sh[32];
+  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  for (uint32_t L = L0; L < t.levels; L++) {
+    const uint32_t half_log = t.levels - L - 1;
+    const uint32_t per_set = (L + 1) << half_log;
+    for (uint32_t i = tid; i < per_set; i += blockDim.x) tree_item(buf, t, L, w, i >> half_log, i & ((1u << half_log) - 1));
     __syncthreads();
   }
-  if (tid == 0) st_xyzz(out + blockIdx.x, ld_xyzz(&sh[0]));
-}
-
-// F[w] = G[w] + sum_l 2^l A_l[w]: one block per set, thread l doubles (sum of its plane's chunk sums) l times,
-// then a tree over the planes.  part is [levels * nsets][chunks]; g points at X^levels (one entry per set).
-__global__ void __launch_bounds__(32) msm_reduce_combine_kernel(const G1Xyzz* __restrict__ part, uint32_t chunks,
-                                                                const G1Xyzz* __restrict__ g, uint32_t levels, uint32_t nsets,
-                                                                G1Xyzz* __restrict__ out) {
-  __shared__ G1Xyzz sh[32];
-  const uint32_t w = blockIdx.x, l = threadIdx.x;
-  G1Xyzz acc = G1Xyzz::infinity();
-  if (l < levels) {
-    const G1Xyzz* p = part + ((size_t)l * nsets + w) * chunks;
-    for (uint32_t k = 0; k < chunks; k++) {
-      G1Xyzz q = ld_xyzz(p + k);
-      xyzz_add(acc, q);
+  // F[w] = G[w] + sum_l 2^l A_l[w]
+  if (tid < 32) {
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (tid + 1 < t.levels) {  // A_l = P_l^levels[0]: written by the last step into half (levels - l) & 1
+      const uint32_t oh = (t.levels - tid) & 1u;
+      acc = ld_xyzz(buf + t.poff[tid] + ((size_t)oh * t.nsets + w) * tree_plane_len(t, tid));
+    } else if (tid + 1 == t.levels) {
+      acc = ld_xyzz(buf + t.off[tid] + (size_t)w * 2 + 1);
+    } else if (tid == t.levels) {
+      acc = ld_xyzz(buf + t.off[t.levels] + w);
     }
-    for (uint32_t k = 0; k < l; k++) acc = xyzz_dbl(acc);
-  } else if (l == levels) {
-    acc = ld_xyzz(g + w);
+    if (tid < t.levels)
+      for (uint32_t k = 0; k < tid; k++) acc = xyzz_dbl(acc);
+    st_xyzz(&sh[tid], acc);
   }
-  st_xyzz(&sh[l], acc);
   __syncthreads();
   for (uint32_t s = 16; s > 0; s >>= 1) {
-    if (l < s) {
-      G1Xyzz a = ld_xyzz(&sh[l]), b = ld_xyzz(&sh[l + s]);
+    if (tid < s) {
+      G1Xyzz a = ld_xyzz(&sh[tid]), b = ld_xyzz(&sh[tid + s]);
       xyzz_add(a, b);
-      st_xyzz(&sh[l], a);
+      st_xyzz(&sh[tid], a);
     }
     __syncthreads();
   }
-  if (l == 0) st_xyzz(out + w, ld_xyzz(&sh[0]));
+  if (tid == 0) st_xyzz(out + w, ld_xyzz(&sh[0]));
 }
 
 // 2^c * P for every point of one table window (fixed-base precomputation)
@@ -565,16 +548,11 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
   ZKP_TRY(m.bucket_start.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.bucket_end.reserve((size_t)total_buckets * 4));
   ZKP_TRY(m.misc.reserve((size_t)(total_buckets + 1) * 12 + (HEAVY_CAP + 1) * 4));
-  // stage-1 blocks per (level, set): enough for ~2 waves over all sets at the widest level, never more than one
-  // block per min_chunk entries
-  const uint32_t min_chunk = ((size_t)nbuckets * nsets <= ((size_t)1 << 17)) ? SUM_CHUNK_SMALL : SUM_CHUNK_LARGE;
-  uint32_t chunks = ((nbuckets >> 1) + min_chunk - 1) / min_chunk;
-  uint32_t chunk_cap = 1200 / nsets;
-  if (chunk_cap > SUM_CHUNKS) chunk_cap = SUM_CHUNKS;
-  if (chunk_cap < 1) chunk_cap = 1;
-  if (chunks > chunk_cap) chunks = chunk_cap;
-  if (chunks < 1) chunks = 1;
-  ZKP_TRY(m.seg_out.reserve((lvl_elems * nsets + ((size_t)chunks + 1) * (c - 1) * nsets) * sizeof(G1Xyzz)));
+  // plane ping-pong buffers of the reduction tree: 2 * max(nbuckets >> (p + 2), 1) entries per set and plane
+  size_t plane_elems = 0;
+  for (uint32_t p = 0; p + 1 < levels; p++) plane_elems += 2 * (size_t)((nbuckets >> (p + 2)) ? (nbuckets >> (p + 2)) : 1);
+  if ((lvl_elems + plane_elems) * nsets >= ((size_t)1 << 32)) return ZKP_ERR_INVALID_ARG;
+  ZKP_TRY(m.seg_out.reserve((lvl_elems + plane_elems) * nsets * sizeof(G1Xyzz)));
   ZKP_TRY(m.win_out.reserve((size_t)(nsets + 1) * sizeof(G1Xyzz)));
   uint32_t* keys_a = m.keys_a.as<uint32_t>();
   uint32_t* keys_b = m.keys_b.as<uint32_t>();
@@ -700,36 +678,33 @@ int msm_run_multi_dev(Ctx* ctx, const Fr* const* scalars_list, const size_t* n_l
              (const G1Xyzz*)partials, (const uint32_t*)task_off, (const uint32_t*)nfold, total_buckets, lvl_buf);
   ctx->msm_launches += 2;
   {
-    G1Xyzz* sum_scratch = lvl_buf + lvl_elems * nsets;
-    RedLevels lv;
-    memset(&lv, 0, sizeof(lv));
+    RedTree t;
+    memset(&t, 0, sizeof(t));
+    t.m = nbuckets;
+    t.levels = levels;
+    t.nsets = nsets;
     size_t off = 0;
     for (uint32_t l = 0; l <= levels; l++) {
-      lv.off[l] = (uint32_t)off;
-      lv.m[l] = nbuckets >> l;
+      t.off[l] = (uint32_t)off;
       off += (size_t)(nbuckets >> l) * nsets;
     }
-    off = lv.off[levels];
-    uint32_t l = 0;
-    for (; l < levels && lv.m[l] > TAIL_M; l++) {  // wide levels: one launch each
-      const uint32_t pairs = (lv.m[l] >> 1) * nsets;
-      ZKP_LAUNCH_NOSYNC(msm_pair_add_kernel, dim3((pairs + RED_THREADS - 1) / RED_THREADS), dim3(RED_THREADS), 0, st,
-                 (const G1Xyzz*)(lvl_buf + lv.off[l]), pairs, lvl_buf + lv.off[l + 1]);
+    off = lvl_elems * nsets;
+    for (uint32_t p = 0; p + 1 < levels; p++) {
+      t.poff[p] = (uint32_t)off;
+      off += 2 * (size_t)((nbuckets >> (p + 2)) ? (nbuckets >> (p + 2)) : 1) * nsets;
+    }
+    uint32_t L = 0;
+    for (; L < levels; L++) {  // wide steps: one launch each
+      const size_t per_set = (size_t)(L + 1) * (nbuckets >> (L + 1));
+      if (L > 0 && per_set <= TAIL_ITEMS) break;
+      const size_t items = per_set * nsets;
+      ZKP_LAUNCH_NOSYNC(msm_tree_step_kernel, dim3((unsigned)((items + RED_THREADS - 1) / RED_THREADS)), dim3(RED_THREADS), 0, st,
+                        lvl_buf, t, L);
       ctx->msm_launches++;
     }
-    if (l < levels) {  // the rest in one launch, one block per set
-      ZKP_LAUNCH(msm_pair_tail_kernel, dim3(nsets), dim3(RED_THREADS), 0, st, lvl_buf, lv, l, levels);
-      ctx->msm_launches++;
-    }
-    // A_l = sum of the odd entries of X^l, every level and set in one launch; the combine finishes the sums
-    G1Xyzz* plane = sum_scratch + (size_t)chunks * levels * nsets;  // [levels * nsets]
-    ZKP_LAUNCH(msm_plane_sum_kernel, dim3(chunks, levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)lvl_buf, lv,
-               nsets, min_chunk, sum_scratch);
-    ZKP_LAUNCH(msm_plane_sum2_kernel, dim3(levels * nsets), dim3(RED_THREADS), 0, st, (const G1Xyzz*)sum_scratch, chunks,
-               plane);
-    ZKP_LAUNCH(msm_reduce_combine_kernel, dim3(nsets), dim3(32), 0, st, (const G1Xyzz*)plane, 1u,
-               (const G1Xyzz*)(lvl_buf + off), levels, nsets, win_out);
-    ctx->msm_launches += 3;
+    // the narrow steps and the combine in one launch, one block per set
+    ZKP_LAUNCH(msm_tree_tail_kernel, dim3(nsets), dim3(TAIL_THREADS), 0, st, lvl_buf, t, L, win_out);
+    ctx->msm_launches++;
   }
   phase_mark(ctx, 5);
   ctx->msm_launches += ctx->sort_launches;  // pair sort, task sort, task-offset scan
