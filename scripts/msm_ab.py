@@ -28,7 +28,7 @@ bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
 eng.generate_bases_dev(0xB200, n, bases)
 scalars = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device="cuda")
 eng.srs_upload_dev(bases, n)
-eng.srs_precompute(0)
+eng.srs_precompute(int(os.environ.get("ZKP_C", "0")))
 ref = None
 for r in rounds_list:
     eng.set_msm_affine(r)

@@ -763,10 +763,12 @@ int zkp_fr_eval_dev(zkp_ctx* h, uint32_t count, const void* const* polys_dev, co
                     uint64_t* out) {
   ZKP_ENTER(h);
   if (count >= Ctx::EVAL_SLOTS || (count && (!polys_dev || !lens || !xs || !out))) return ZKP_ERR_INVALID_ARG;
+  Fr pts[Ctx::EVAL_SLOTS];
   for (uint32_t k = 0; k < count; k++) {
     if (lens[k] && !polys_dev[k]) return ZKP_ERR_INVALID_ARG;
-    ZKP_TRY(fr_eval_queue_dev(c, (const Fr*)polys_dev[k], lens[k], fr_of(xs + 4 * k), k));
+    pts[k] = fr_of(xs + 4 * k);
   }
+  ZKP_TRY(fr_eval_batch_dev(c, count, reinterpret_cast<const Fr* const*>(polys_dev), lens, pts));
   return fr_eval_fetch(c, (Fr*)out, count);
 }
 

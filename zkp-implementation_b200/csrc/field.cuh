@@ -604,7 +604,9 @@ ZKP_HD_NOINLINE Fp<P> fp_inv(const Fp<P>& a) {
 template <class P>
 ZKP_HD_NOINLINE Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
   Fp<P> r = Fp<P>::one();
-  for (int i = 63; i >= 0; i--) {
+  int top = 63;
+  while (top >= 0 && !((e >> top) & 1)) top--;  // nothing to square above the leading bit
+  for (int i = top; i >= 0; i--) {
     r = fp_sqr(r);
     if ((e >> i) & 1) r = fp_mul(r, a);
   }

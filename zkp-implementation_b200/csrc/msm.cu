@@ -393,17 +393,21 @@ __global__ void __launch_bounds__(128) msm_shift_window_kernel(const G1Affine* _
 // Host orchestration
 // ------------------------------------------------------------------------------------------------
 // cost model in mixed-add units: n*W additions + the reduction's cost per bucket.  Fixed-base mode: measured 1.27 ns per
-// bucket on top of a size-independent part (reduce phase 1.5 ms at 2^17 buckets, 4.0 ms at 2^21) = 3.5 additions of
+// bucket on top of a size-independent part (reduce phase 1.5 ms at 2^17 buckets, 4.0 ms at 2^21; 1.3 / 3.5 ms with the fused
+// tree, scripts/window_sweep.py) = 3 additions of
 // 0.36 ns; windowed mode keeps the round-1 figure (every window has its own bucket set and the Horner tail).
 static uint32_t choose_window_bits(size_t n, bool fixed) {
   uint32_t best = 4;
   double best_cost = 1e300;
   const uint32_t cmax = fixed ? 24 : 20;
-  const double per_bucket = fixed ? 3.5 : 8.0;
+  const double per_bucket = fixed ? 3.0 : 8.0;
   for (uint32_t c = 4; c <= cmax; c++) {
     const uint32_t W = 255 / c + 1;
     const double nb = (double)(1u << (c - 1)) * (fixed ? 1 : W);
-    const double cost = (double)n * W + per_bucket * nb;
+    double cost = (double)n * W + per_bucket * nb;
+    // a top window of only a few bits (c = 14: 3, c = 15: 0 + the carry) piles all n points into a handful of buckets: long
+    // runs to split and fold (2^14..2^16: c = 14 / 15 measured 10-20 % slower than c = 13 / 16)
+    if (fixed && 255 - (int)(c * (W - 1)) < 6) cost += (double)n;
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;

@@ -202,10 +202,22 @@ int fr_add_at_dev(Ctx* ctx, Fr* data, const SparseAddArgs& a) {
 }
 
 // ---- evaluation -----------------------------------------------------------------------------------
-// partial[b] = sum over the block's chunks of (Horner of the chunk) * x^(chunk start)
-__global__ void __launch_bounds__(PT) fr_eval_partial_kernel(const Fr* c, size_t n, Fr x, Fr* partial) {
+// All evaluations of one call (the prover's seven openings at zeta / zeta omega) run as ONE launch pair: block (bx, k)
+// handles chunk bx of polynomial k.  partial[k][bx] = sum over the block's threads of (Horner of 32 coefficients) *
+// x^(first index); thread-level cost = 32 products + one exponentiation over the bits of the index.
+struct EvalBatch {
+  const Fr* c[Ctx::EVAL_SLOTS];
+  size_t n[Ctx::EVAL_SLOTS];
+  Fr x[Ctx::EVAL_SLOTS];
+};
+
+__global__ void __launch_bounds__(PT) fr_eval_partial_kernel(EvalBatch b, Fr* partial) {
   __shared__ __align__(16) Fr sh[PT];
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, k = blockIdx.y;
+  const size_t n = b.n[k];
+  if ((size_t)blockIdx.x * (PT * EV_CHUNK) >= n) return;  // block-uniform: shorter polynomial of the batch
+  const Fr* c = b.c[k];
+  const Fr x = b.x[k];
   const size_t t = (size_t)blockIdx.x * blockDim.x + tid;
   const size_t start = t * EV_CHUNK;
   Fr acc = Fr::zero();
@@ -220,38 +232,46 @@ __global__ void __launch_bounds__(PT) fr_eval_partial_kernel(const Fr* c, size_t
     if (tid < s) st_fr(&sh[tid], fp_add(ld_fr(&sh[tid]), ld_fr(&sh[tid + s])));
     __syncthreads();
   }
-  if (tid == 0) st_fr(partial + blockIdx.x, ld_fr(&sh[0]));
+  if (tid == 0) st_fr(partial + (size_t)k * Ctx::EVAL_PARTIALS + blockIdx.x, ld_fr(&sh[0]));
 }
 
-__global__ void __launch_bounds__(PT) fr_sum_kernel(const Fr* in, size_t n, Fr* out) {
+// out[k] = sum of polynomial k's block partials (0 for an empty polynomial)
+__global__ void __launch_bounds__(PT) fr_sum_kernel(const Fr* partial, EvalBatch b, Fr* out) {
   __shared__ __align__(16) Fr sh[PT];
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, k = blockIdx.x;
+  const size_t nb = (b.n[k] + (size_t)PT * EV_CHUNK - 1) / ((size_t)PT * EV_CHUNK);
+  const Fr* in = partial + (size_t)k * Ctx::EVAL_PARTIALS;
   Fr acc = Fr::zero();
-  for (size_t i = tid; i < n; i += PT) acc = fp_add(acc, ld_fr(in + i));
+  for (size_t i = tid; i < nb; i += PT) acc = fp_add(acc, ld_fr(in + i));
   st_fr(&sh[tid], acc);
   __syncthreads();
   for (uint32_t s = PT / 2; s > 0; s >>= 1) {
     if (tid < s) st_fr(&sh[tid], fp_add(ld_fr(&sh[tid]), ld_fr(&sh[tid + s])));
     __syncthreads();
   }
-  if (tid == 0) st_fr(out, ld_fr(&sh[0]));
+  if (tid == 0) st_fr(out + k, ld_fr(&sh[0]));
 }
 
-// Queue one evaluation; the value lands in slot `slot` of the context's result area (read back in bulk).
-int fr_eval_queue_dev(Ctx* ctx, const Fr* coeffs, size_t n, const Fr& x, uint32_t slot) {
-  if (slot >= Ctx::EVAL_SLOTS) return ZKP_ERR_INVALID_ARG;
+// Evaluate `count` polynomials (device coefficients, natural order) at their points; the values land in the context's
+// result area, slot k, and are read back in bulk by fr_eval_fetch.
+int fr_eval_batch_dev(Ctx* ctx, uint32_t count, const Fr* const* coeffs, const size_t* lens, const Fr* xs) {
+  if (count > Ctx::EVAL_SLOTS) return ZKP_ERR_INVALID_ARG;
+  if (!count) return ZKP_OK;
   ZKP_TRY(ctx->eval_out.reserve(Ctx::EVAL_SLOTS * sizeof(Fr)));
-  Fr* out = ctx->eval_out.as<Fr>() + slot;
-  if (!n) return rt::dev_memset(out, 0, sizeof(Fr), ctx->stream);
-  const unsigned nb = blocks_for(n, PT * EV_CHUNK);
-  // every queued evaluation needs its own partial area until the results are fetched
-  const size_t need = ((size_t)slot + 1) * Ctx::EVAL_PARTIALS * sizeof(Fr);
-  if (nb > Ctx::EVAL_PARTIALS) return ZKP_ERR_INVALID_ARG;
   ZKP_TRY(ctx->eval_partials.reserve(Ctx::EVAL_SLOTS * Ctx::EVAL_PARTIALS * sizeof(Fr)));
-  (void)need;
-  Fr* partial = ctx->eval_partials.as<Fr>() + (size_t)slot * Ctx::EVAL_PARTIALS;
-  ZKP_LAUNCH(fr_eval_partial_kernel, dim3(nb), dim3(PT), 0, ctx->stream, coeffs, n, x, partial);
-  ZKP_LAUNCH(fr_sum_kernel, dim3(1), dim3(PT), 0, ctx->stream, (const Fr*)partial, (size_t)nb, out);
+  EvalBatch b;
+  memset(&b, 0, sizeof(b));
+  unsigned nb_max = 1;
+  for (uint32_t k = 0; k < count; k++) {
+    const unsigned nb = lens[k] ? blocks_for(lens[k], PT * EV_CHUNK) : 0u;
+    if (nb > Ctx::EVAL_PARTIALS) return ZKP_ERR_INVALID_ARG;
+    if (nb > nb_max) nb_max = nb;
+    b.c[k] = coeffs[k];
+    b.n[k] = lens[k];
+    b.x[k] = xs[k];
+  }
+  ZKP_LAUNCH(fr_eval_partial_kernel, dim3(nb_max, count), dim3(PT), 0, ctx->stream, b, ctx->eval_partials.as<Fr>());
+  ZKP_LAUNCH(fr_sum_kernel, dim3(count), dim3(PT), 0, ctx->stream, (const Fr*)ctx->eval_partials.as<Fr>(), b, ctx->eval_out.as<Fr>());
   return rt::check_last();
 }
 

@@ -43,7 +43,7 @@ int fr_batch_inverse_dev(Ctx* ctx, Fr* data, size_t n);
 int fr_scan_dev(Ctx* ctx, Fr* data, size_t n, int op /* 0 mul, 1 add */, bool reverse);
 int fr_lincomb_dev(Ctx* ctx, Fr* out, size_t out_len, const LincombArgs& a);
 int fr_add_at_dev(Ctx* ctx, Fr* data, const SparseAddArgs& a);
-int fr_eval_queue_dev(Ctx* ctx, const Fr* coeffs, size_t n, const Fr& x, uint32_t slot);
+int fr_eval_batch_dev(Ctx* ctx, uint32_t count, const Fr* const* coeffs, const size_t* lens, const Fr* xs);
 int fr_eval_fetch(Ctx* ctx, Fr* out_host, uint32_t count);
 int fr_trimmed_len_dev(Ctx* ctx, const Fr* coeffs, size_t n, size_t* out_len);
 int plonk_numden_dev(Ctx* ctx, const PlonkNumDenArgs& p);
