@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import zkp_implementation_b200 as z
 from oracle import coracle as c
-eng = z.Engine(0); eng.set_stream(torch.cuda.current_stream().cuda_stream)
+eng = z.Engine(0, lib_path=os.environ.get("ZKP_LIB")); eng.set_stream(torch.cuda.current_stream().cuda_stream)
 F = z.fields
 a = F.random_fr_mont(1, 1 << 20)
 t = torch.from_numpy(a.view(np.int64)).cuda()

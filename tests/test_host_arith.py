@@ -23,11 +23,15 @@ def test_field_ops(hostlib, zkp, name):
     rinv = pow(R, -1, mod)
     rnd = random.Random(1)
     cases = [(0, 0), (0, 1), (mod - 1, mod - 1), (mod - 1, 1), (1, mod - 1), (R % mod, R % mod)]
+    # half-limb patterns: the Karatsuba halves' differences change sign / vanish, carries run through whole halves
+    for hi in ("ffffffff", "00000000", "80000000", "00000001", "7fffffff"):
+        for lo in ("ffffffff", "00000000", "80000000", "00000001"):
+            cases.append((int(hi * (n // 2) + lo * (n // 2), 16) % mod, int(lo * (n // 2) + hi * (n // 2), 16) % mod))
     cases += [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(1500)]
     out = (ctypes.c_uint32 * n)()
     for a, b in cases:
         for op, exp in ((0, (a + b) % mod), (1, (a - b) % mod), (2, a * b * rinv % mod), (3, a * b * rinv % mod),
-                        (7, a * b * rinv % mod)):
+                        (7, a * b * rinv % mod), (10, a * b * rinv % mod)):  # 10 = Karatsuba + separated reduction (experiment knob)
             assert fn(op, _pack(a, n), _pack(b, n), out) == 0
             assert _unpack(out) == exp, (name, op, hex(a), hex(b))
     # dedicated squaring (triangular carry-chain rows): edge values with every top / bottom bit pattern, then random

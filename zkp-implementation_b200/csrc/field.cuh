@@ -427,6 +427,197 @@ ZKP_HD Fp<P> fp_mul_chain(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---- Karatsuba product + separated reduction (experiment knob -DZKP_KARATSUBA) --------------------------------
+// The interleaved multiplier above spends n^2 limb products on a*b and n^2 (Fr: n (n - 2)) on the reduction rows.  The
+// a*b part splits: with a = aL + aH 2^(16 n), b likewise,
+//   a b = z0 + (z0 + z2 + (aL - aH)(bH - bL)) 2^(16 n) + z2 2^(32 n),  z0 = aL bL,  z2 = aH bH
+// -- three half-size products instead of four (Fq: 108 instead of 144 limb products, Fr: 48 instead of 64), paid for
+// with add-with-carry instructions on the ALU pipe, whose issue slots the multiplier-bound kernels leave idle.  The
+// price is that the product must exist as 2n plain limbs before the reduction, so the reduction rows run on their own:
+// accumulators U (pairs at even limbs) and V (pairs at odd limbs) indexed by ABSOLUTE limb -- the unrolled code needs no
+// shifting -- with the upper half of the product fed in one limb per row so that every carry lands in a limb that holds
+// only earlier carries (no long ripples), and the carry out of the cleared limb kept in a small separate word.
+namespace detail {
+// out[2h] = x[h] * y[h], h even: E holds the pairs at even limbs, O the pairs at odd limbs (O[k] is limb k + 1)
+template <int h>
+ZKP_HD void mul_half(uint32_t* out, const uint32_t* x, const uint32_t* y) {
+  static_assert(h % 2 == 0, "even half size");
+  uint32_t E[2 * h], O[2 * h];
+#pragma unroll
+  for (int k = 0; k < 2 * h; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < h; i++) {
+    const uint32_t yi = y[i];
+    if ((i & 1) == 0) {
+      E[i] = ptx::mad_lo_cc(x[0], yi, E[i]);
+      E[i + 1] = ptx::madc_hi_cc(x[0], yi, E[i + 1]);
+#pragma unroll
+      for (int j = 2; j < h; j += 2) {
+        E[i + j] = ptx::madc_lo_cc(x[j], yi, E[i + j]);
+        E[i + j + 1] = ptx::madc_hi_cc(x[j], yi, E[i + j + 1]);
+      }
+      E[i + h] = ptx::addc(E[i + h], 0u);
+      O[i] = ptx::mad_lo_cc(x[1], yi, O[i]);
+      O[i + 1] = ptx::madc_hi_cc(x[1], yi, O[i + 1]);
+#pragma unroll
+      for (int j = 3; j < h; j += 2) {
+        O[i + j - 1] = ptx::madc_lo_cc(x[j], yi, O[i + j - 1]);
+        O[i + j] = ptx::madc_hi_cc(x[j], yi, O[i + j]);
+      }
+      O[i + h] = ptx::addc(O[i + h], 0u);
+    } else {
+      O[i - 1] = ptx::mad_lo_cc(x[0], yi, O[i - 1]);
+      O[i] = ptx::madc_hi_cc(x[0], yi, O[i]);
+#pragma unroll
+      for (int j = 2; j < h; j += 2) {
+        O[i + j - 1] = ptx::madc_lo_cc(x[j], yi, O[i + j - 1]);
+        O[i + j] = ptx::madc_hi_cc(x[j], yi, O[i + j]);
+      }
+      O[i + h - 1] = ptx::addc(O[i + h - 1], 0u);
+      E[i + 1] = ptx::mad_lo_cc(x[1], yi, E[i + 1]);
+      E[i + 2] = ptx::madc_hi_cc(x[1], yi, E[i + 2]);
+#pragma unroll
+      for (int j = 3; j < h; j += 2) {
+        E[i + j] = ptx::madc_lo_cc(x[j], yi, E[i + j]);
+        E[i + j + 1] = ptx::madc_hi_cc(x[j], yi, E[i + j + 1]);
+      }
+      if (i + h + 1 < 2 * h) E[i + h + 1] = ptx::addc(E[i + h + 1], 0u);  // the last row ends at the top limb: no carry
+    }
+  }
+  out[0] = E[0];
+  out[1] = ptx::add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 2 * h - 1; k++) out[k] = ptx::addc_cc(E[k], O[k - 1]);
+  out[2 * h - 1] = ptx::addc(E[2 * h - 1], O[2 * h - 2]);
+}
+
+// d = |x - y| over h limbs; returns the mask of x < y (0 or 0xffffffff)
+template <int h>
+ZKP_HD uint32_t abs_diff(uint32_t* d, const uint32_t* x, const uint32_t* y) {
+  d[0] = ptx::sub_cc(x[0], y[0]);
+#pragma unroll
+  for (int k = 1; k < h; k++) d[k] = ptx::subc_cc(x[k], y[k]);
+  const uint32_t m = ptx::subc(0u, 0u);
+  d[0] = ptx::add_cc(d[0] ^ m, m & 1u);
+#pragma unroll
+  for (int k = 1; k < h - 1; k++) d[k] = ptx::addc_cc(d[k] ^ m, 0u);
+  d[h - 1] = ptx::addc(d[h - 1] ^ m, 0u);
+  return m;
+}
+
+// r = T / 2^(32 n) mod p for a 2n-limb T < p 2^(32 n); result < 2p in n limbs
+template <class P>
+ZKP_HD void redc_wide(uint32_t* r, const uint32_t* T) {
+  constexpr int n = P::N;
+  uint32_t U[2 * n + 2], V[2 * n + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * n + 2; k++) { U[k] = (k < n) ? T[k] : 0u; V[k] = 0; }
+  uint32_t cy = 0;
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    // feed the next limb of the upper half
+    U[n + i] = ptx::add_cc(U[n + i], T[n + i]);
+    U[n + i + 1] = ptx::addc(U[n + i + 1], 0u);
+    const uint32_t s = U[i] + V[i] + cy;
+    uint32_t* X = (i & 1) ? V : U;  // pairs aligned with limb i
+    uint32_t* Y = (i & 1) ? U : V;  // pairs aligned with limb i + 1
+    if constexpr (P::LOW_LIMBS_SPECIAL) {
+#if defined(__CUDA_ARCH__)
+      const uint32_t mi = s * zkp_opaque_minus_one;
+#else
+      const uint32_t mi = 0u - s;
+#endif
+      // mod[0] = 1: an addition; mod[1] = 2^32 - 1: (hi, lo) = (mi - [mi != 0], -mi)
+      X[i] = ptx::add_cc(X[i], mi);
+      X[i + 1] = ptx::addc_cc(X[i + 1], 0u);
+#pragma unroll
+      for (int j = 2; j < n; j += 2) {
+        X[i + j] = ptx::madc_lo_cc(P::mod(j), mi, X[i + j]);
+        X[i + j + 1] = ptx::madc_hi_cc(P::mod(j), mi, X[i + j + 1]);
+      }
+      X[i + n] = ptx::addc_cc(X[i + n], 0u);
+      X[i + n + 1] = ptx::addc(X[i + n + 1], 0u);
+      const uint32_t lo1 = 0u - mi;
+      const uint32_t hi1 = mi - (mi != 0u ? 1u : 0u);
+      Y[i + 1] = ptx::add_cc(Y[i + 1], lo1);
+      Y[i + 2] = ptx::addc_cc(Y[i + 2], hi1);
+#pragma unroll
+      for (int j = 3; j < n; j += 2) {
+        Y[i + j] = ptx::madc_lo_cc(P::mod(j), mi, Y[i + j]);
+        Y[i + j + 1] = ptx::madc_hi_cc(P::mod(j), mi, Y[i + j + 1]);
+      }
+      Y[i + n + 1] = ptx::addc(Y[i + n + 1], 0u);
+    } else {
+      const uint32_t mi = s * P::M0;
+      X[i] = ptx::mad_lo_cc(P::mod(0), mi, X[i]);
+      X[i + 1] = ptx::madc_hi_cc(P::mod(0), mi, X[i + 1]);
+#pragma unroll
+      for (int j = 2; j < n; j += 2) {
+        X[i + j] = ptx::madc_lo_cc(P::mod(j), mi, X[i + j]);
+        X[i + j + 1] = ptx::madc_hi_cc(P::mod(j), mi, X[i + j + 1]);
+      }
+      X[i + n] = ptx::addc_cc(X[i + n], 0u);
+      X[i + n + 1] = ptx::addc(X[i + n + 1], 0u);
+      Y[i + 1] = ptx::mad_lo_cc(P::mod(1), mi, Y[i + 1]);
+      Y[i + 2] = ptx::madc_hi_cc(P::mod(1), mi, Y[i + 2]);
+#pragma unroll
+      for (int j = 3; j < n; j += 2) {
+        Y[i + j] = ptx::madc_lo_cc(P::mod(j), mi, Y[i + j]);
+        Y[i + j + 1] = ptx::madc_hi_cc(P::mod(j), mi, Y[i + j + 1]);
+      }
+      Y[i + n + 1] = ptx::addc(Y[i + n + 1], 0u);
+    }
+    // limb i is now 0 mod 2^32: keep its carry (0, 1 or 2)
+    uint32_t t = ptx::add_cc(U[i], V[i]);
+    const uint32_t c1 = ptx::addc(0u, 0u);
+    t = ptx::add_cc(t, cy);
+    cy = ptx::addc(c1, 0u);
+    (void)t;
+  }
+  r[0] = ptx::add_cc(U[n], V[n]);
+#pragma unroll
+  for (int k = 1; k < n - 1; k++) r[k] = ptx::addc_cc(U[n + k], V[n + k]);
+  r[n - 1] = ptx::addc(U[2 * n - 1], V[2 * n - 1]);
+  r[0] = ptx::add_cc(r[0], cy);
+#pragma unroll
+  for (int k = 1; k < n - 1; k++) r[k] = ptx::addc_cc(r[k], 0u);
+  r[n - 1] = ptx::addc(r[n - 1], 0u);
+}
+}  // namespace detail
+
+template <class P>
+ZKP_HD Fp<P> fp_mul_kara(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int n = P::N, h = n / 2;
+  uint32_t T[2 * n], z1[n], mid[n], da[h], db[h];
+  detail::mul_half<h>(T, a.v, b.v);              // z0
+  detail::mul_half<h>(T + n, a.v + h, b.v + h);  // z2
+  const uint32_t ma = detail::abs_diff<h>(da, a.v, a.v + h);      // |aL - aH|
+  const uint32_t mb = detail::abs_diff<h>(db, b.v + h, b.v);      // |bH - bL|
+  detail::mul_half<h>(z1, da, db);
+  const uint32_t sgn = ma ^ mb;  // all ones: (aL - aH)(bH - bL) = -z1
+  // mid = z0 + z2 + sgn z1  (n limbs + a small top word; never negative: it is aL bH + aH bL)
+  mid[0] = ptx::add_cc(T[0], T[n]);
+#pragma unroll
+  for (int k = 1; k < n; k++) mid[k] = ptx::addc_cc(T[k], T[n + k]);
+  uint32_t midc = ptx::addc(0u, 0u);
+  (void)ptx::add_cc(sgn, sgn);  // carry = 1 when subtracting: ~z1 + 1
+#pragma unroll
+  for (int k = 0; k < n; k++) mid[k] = ptx::addc_cc(mid[k], z1[k] ^ sgn);
+  midc = ptx::addc(midc, sgn);
+  // T += mid 2^(32 h)
+  T[h] = ptx::add_cc(T[h], mid[0]);
+#pragma unroll
+  for (int k = 1; k < n; k++) T[h + k] = ptx::addc_cc(T[h + k], mid[k]);
+  T[h + n] = ptx::addc_cc(T[h + n], midc);
+#pragma unroll
+  for (int k = h + n + 1; k < 2 * n - 1; k++) T[k] = ptx::addc_cc(T[k], 0u);
+  T[2 * n - 1] = ptx::addc(T[2 * n - 1], 0u);
+  Fp<P> r;
+  detail::redc_wide<P>(r.v, T);
+  fp_final_sub(r);
+  return r;
+}
+
 // ---- dedicated squaring in the same carry-chain form ---------------------------------------------------
 // a^2 = sum_i a_i^2 2^(64 i) + 2 sum_{i<j} a_i a_j 2^(32 (i+j)).  Row i of the interleaved (CIOS) schedule multiplies
 // the scalar a_i by the vector  u_i = [a_i, 2 a_(i+1), 2 a_(i+2), ...]  -- the doubled higher limbs, with the bit
@@ -555,6 +746,12 @@ ZKP_HD Fp<P> fp_sqr_chain(const Fp<P>& a) {
 template <class P>
 ZKP_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if ZKP_PTX_DEVICE || defined(ZKP_FIELD_CHAIN_ON_HOST)
+#if defined(ZKP_KARATSUBA_FQ)
+  if constexpr (P::N == 12) return fp_mul_kara(a, b);
+#endif
+#if defined(ZKP_KARATSUBA_FR)
+  if constexpr (P::N == 8) return fp_mul_kara(a, b);
+#endif
   return fp_mul_chain(a, b);
 #elif defined(ZKP_HOST_MUL64) && !defined(ZKP_FIELD_PORTABLE)
   return fp_mul_host64(a, b);
