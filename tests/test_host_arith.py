@@ -51,17 +51,21 @@ def test_field_ops(hostlib, zkp, name):
     assert _unpack(out) == a
 
 
-def test_fq_inverse_by_division_steps(hostlib, zkp):
-    """csrc/inv_gcd.cuh (the inversion of the batched-affine MSM rounds): safegcd division steps against pow(a, -1, p)
-    and against the Fermat ladder it replaces -- small values, values next to p, every single-bit value (long runs of
-    even steps), all-ones patterns, 0 -> 0, and random residues."""
+@pytest.mark.parametrize("name", ["fr", "fq"])
+def test_inverse_by_division_steps(hostlib, zkp, name):
+    """csrc/inv_gcd.cuh (the inversions of the batched-affine MSM rounds, of the batch normalisations and of the prover's
+    batch inverse): safegcd division steps against pow(a, -1, p) and against the Fermat ladder they replace -- small
+    values, values next to p, every single-bit value (long runs of even steps), all-ones patterns, 0 -> 0, random residues."""
     F = zkp.fields
-    fn, mod, n, R = hostlib.zkp_t_fq_op, F.FQ_MODULUS, 12, F.FQ_R
+    fn, mod, n, R = ((hostlib.zkp_t_fr_op, F.FR_MODULUS, 8, F.FR_R) if name == "fr"
+                     else (hostlib.zkp_t_fq_op, F.FQ_MODULUS, 12, F.FQ_R))
+    bits = mod.bit_length()
     rnd = random.Random(7)
-    vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, R % mod, pow(R, -1, mod), (1 << 380), (1 << 380) - 1,
-            int("55" * 47, 16) % mod, int("aa" * 47, 16) % mod]
-    vals += [1 << k for k in range(381)] + [(mod - (1 << k)) % mod for k in range(381)]
+    vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, R % mod, pow(R, -1, mod), 1 << (bits - 1), (1 << (bits - 1)) - 1,
+            int("55" * (4 * n), 16) % mod, int("aa" * (4 * n), 16) % mod]
+    vals += [(1 << k) % mod for k in range(bits)] + [(mod - (1 << k)) % mod for k in range(bits)]
     vals += [rnd.randrange(1, mod) for _ in range(3000)]
+    vals = [v for v in vals if v]
     out, out2 = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
     for a in vals:  # `a` is the stored (Montgomery) residue: a = x R, expected x^-1 R = a^-1 R^2
         assert fn(9, _pack(a, n), None, out) == 0

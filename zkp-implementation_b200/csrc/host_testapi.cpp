@@ -12,7 +12,7 @@ using namespace zkp;
 extern "C" {
 
 // op: 0 add, 1 sub, 2 mul (portable), 3 mul (carry-chain algorithm), 4 inv, 5 to_mont, 6 from_mont, 7 mul (64-bit host CIOS),
-//     8 sqr (dedicated carry-chain squaring), 9 inv by division steps (Fq only, inv_gcd.cuh),
+//     8 sqr (dedicated carry-chain squaring), 9 inv by division steps (inv_gcd.cuh),
 //     10 mul (Karatsuba product + separated reduction, the -DZKP_KARATSUBA_* experiment)
 int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   Fr x, y, r;
@@ -28,6 +28,7 @@ int zkp_t_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 6: r = fp_from_mont(x); break;
     case 7: r = fp_mul_host64(x, y); break;
     case 8: r = fp_sqr_chain(x); break;
+    case 9: r = fr_inv_gcd(x); break;
     case 10: r = fp_mul_kara(x, y); break;
     default: return 1;
   }

@@ -1,4 +1,4 @@
-// Fq inversion by division steps ("safegcd", D. J. Bernstein and B.-Y. Yang, "Fast constant-time gcd computation and
+// Fq / Fr inversion by division steps ("safegcd", D. J. Bernstein and B.-Y. Yang, "Fast constant-time gcd computation and
 // modular inversion", TCHES 2019) instead of Fermat's a^(p-2).
 //
 // Why: every batched-affine round of the MSM (msm_affine.cu) ends in ONE inversion per <= 4096 running products, with one
@@ -23,14 +23,25 @@
 namespace zkp {
 namespace sgcd {
 
-static constexpr int L = 13;
 static constexpr int32_t M30 = 0x3fffffff;
-static constexpr uint32_t P_INV30 = 0x00030003u;  // p^-1 mod 2^30
-static constexpr int CHUNKS = 37;                 // 37 * 30 = 1110 >= 1101
+// Per field: L limbs of 30 bits (values live in (-2p, p): bits of p + 1 + sign), p^-1 mod 2^30, and the number of
+// 30-step chunks that covers floor((49 d + 57) / 17) steps for d = bits of p.
+template <class P> struct Cfg;
+template <> struct Cfg<FqParams> {
+  static constexpr int L = 13;
+  static constexpr uint32_t P_INV30 = 0x00030003u;
+  static constexpr int CHUNKS = 37;  // d = 381: 1101 steps <= 37 * 30
+};
+template <> struct Cfg<FrParams> {
+  static constexpr int L = 9;
+  static constexpr uint32_t P_INV30 = 0x00000001u;  // r = 1 mod 2^32
+  static constexpr int CHUNKS = 25;  // d = 255: 738 steps <= 25 * 30
+};
 
+template <class P>
 ZKP_HD constexpr uint32_t p30(int j) {
   const int bit = 30 * j, w = bit >> 5, s = bit & 31;
-  const uint64_t lo = FqParams::mod(w), hi = (w + 1 < 12) ? FqParams::mod(w + 1) : 0;
+  const uint64_t lo = (w < P::N) ? P::mod(w) : 0, hi = (w + 1 < P::N) ? P::mod(w + 1) : 0;
   return (uint32_t)(((lo | (hi << 32)) >> s) & 0x3fffffffu);
 }
 
@@ -63,6 +74,7 @@ ZKP_HD void divsteps30(int32_t& delta, uint32_t f, uint32_t g, int32_t (&t)[4]) 
 }
 
 // (f, g) <- T (f, g) / 2^30, exact
+template <int L>
 ZKP_HD void update_fg(int32_t (&f)[L], int32_t (&g)[L], const int32_t (&t)[4]) {
   const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
   int64_t cf = u * f[0] + v * g[0], cg = q * f[0] + r * g[0];
@@ -83,7 +95,9 @@ ZKP_HD void update_fg(int32_t (&f)[L], int32_t (&g)[L], const int32_t (&t)[4]) {
 }
 
 // (d, e) <- T (d, e) / 2^30 mod p; d, e stay in (-2p, p)
+template <class P, int L>
 ZKP_HD void update_de(int32_t (&d)[L], int32_t (&e)[L], const int32_t (&t)[4]) {
+  constexpr uint32_t P_INV30 = Cfg<P>::P_INV30;
   const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
   const int32_t sd = d[L - 1] >> 31, se = e[L - 1] >> 31;
   // one p per negative operand keeps the sums from drifting down ...
@@ -92,15 +106,15 @@ ZKP_HD void update_de(int32_t (&d)[L], int32_t (&e)[L], const int32_t (&t)[4]) {
   // ... and the multiple of p that clears the low 30 bits
   md -= (int32_t)((P_INV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
   me -= (int32_t)((P_INV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
-  cd += (int64_t)p30(0) * md;
-  ce += (int64_t)p30(0) * me;
+  cd += (int64_t)p30<P>(0) * md;
+  ce += (int64_t)p30<P>(0) * me;
   cd >>= 30;
   ce >>= 30;
 #pragma unroll
   for (int i = 1; i < L; i++) {
     const int64_t di = d[i], ei = e[i];
-    cd += (int64_t)u * di + (int64_t)v * ei + (int64_t)p30(i) * md;
-    ce += (int64_t)q * di + (int64_t)r * ei + (int64_t)p30(i) * me;
+    cd += (int64_t)u * di + (int64_t)v * ei + (int64_t)p30<P>(i) * md;
+    ce += (int64_t)q * di + (int64_t)r * ei + (int64_t)p30<P>(i) * me;
     d[i - 1] = (int32_t)cd & M30;
     e[i - 1] = (int32_t)ce & M30;
     cd >>= 30;
@@ -110,7 +124,8 @@ ZKP_HD void update_de(int32_t (&d)[L], int32_t (&e)[L], const int32_t (&t)[4]) {
   e[L - 1] = (int32_t)ce;
 }
 
-// limbs 0..11 back into [0, 2^30), the sign stays in limb 12
+// low limbs back into [0, 2^30), the sign stays in the top limb
+template <int L>
 ZKP_HD void carry(int32_t (&x)[L]) {
 #pragma unroll
   for (int i = 0; i < L - 1; i++) {
@@ -120,52 +135,55 @@ ZKP_HD void carry(int32_t (&x)[L]) {
 }
 
 // x in (-2p, p), negated when neg is all ones, brought to [0, p)
+template <class P, int L>
 ZKP_HD void normalize(int32_t (&x)[L], int32_t neg) {
   int32_t add = x[L - 1] >> 31;
 #pragma unroll
-  for (int i = 0; i < L; i++) x[i] += (int32_t)p30(i) & add;
+  for (int i = 0; i < L; i++) x[i] += (int32_t)p30<P>(i) & add;
   carry(x);
 #pragma unroll
   for (int i = 0; i < L; i++) x[i] = (x[i] ^ neg) - neg;
   carry(x);
   add = x[L - 1] >> 31;
 #pragma unroll
-  for (int i = 0; i < L; i++) x[i] += (int32_t)p30(i) & add;
+  for (int i = 0; i < L; i++) x[i] += (int32_t)p30<P>(i) & add;
   carry(x);
 }
 
 }  // namespace sgcd
 
 // 1 / a for a Montgomery residue a (0 -> 0, like the Fermat ladder)
-ZKP_HD_NOINLINE Fq fq_inv_gcd(const Fq& a) {
+template <class P>
+ZKP_HD Fp<P> fp_inv_gcd_impl(const Fp<P>& a) {
   using namespace sgcd;
+  constexpr int L = Cfg<P>::L, N = P::N;
   int32_t f[L], g[L], d[L], e[L];
 #pragma unroll
   for (int j = 0; j < L; j++) {
     const int bit = 30 * j, w = bit >> 5, s = bit & 31;
-    const uint32_t lo = a.v[w], hi = (w + 1 < 12) ? a.v[w + 1] : 0u;
+    const uint32_t lo = (w < N) ? a.v[w < N ? w : 0] : 0u, hi = (w + 1 < N) ? a.v[w + 1 < N ? w + 1 : 0] : 0u;
     const uint32_t x = s ? ((lo >> s) | (hi << (32 - s))) : lo;
     g[j] = (int32_t)(x & (uint32_t)M30);
-    f[j] = (int32_t)p30(j);
+    f[j] = (int32_t)p30<P>(j);
     d[j] = 0;
     e[j] = 0;
   }
   e[0] = 1;
   int32_t delta = 1;
 #pragma unroll 1
-  for (int c = 0; c < CHUNKS; c++) {
+  for (int c = 0; c < Cfg<P>::CHUNKS; c++) {
     uint32_t nz = 0;
 #pragma unroll
     for (int j = 0; j < L; j++) nz |= (uint32_t)g[j];
     if (nz == 0) break;  // g = 0: further steps change neither f nor d
     int32_t t[4];
     divsteps30(delta, (uint32_t)f[0] | ((uint32_t)f[1] << 30), (uint32_t)g[0] | ((uint32_t)g[1] << 30), t);
-    update_de(d, e, t);
-    update_fg(f, g, t);
+    update_de<P, L>(d, e, t);
+    update_fg<L>(f, g, t);
   }
-  normalize(d, f[L - 1] >> 31);  // f = -1: d = -1/a
-  // 13 x 30 bits -> 12 x 32 bits
-  Fq r;
+  normalize<P, L>(d, f[L - 1] >> 31);  // f = -1: d = -1/a
+  // L x 30 bits -> N x 32 bits
+  Fp<P> r;
   {
     uint64_t acc = 0;
     int bits = 0, w = 0;
@@ -173,15 +191,18 @@ ZKP_HD_NOINLINE Fq fq_inv_gcd(const Fq& a) {
     for (int j = 0; j < L; j++) {
       acc |= (uint64_t)(uint32_t)d[j] << bits;
       bits += 30;
-      if (bits >= 32 && w < 12) {
+      if (bits >= 32 && w < N) {
         r.v[w++] = (uint32_t)acc;
         acc >>= 32;
         bits -= 32;
       }
     }
   }
-  const Fq r2 = Fq::r2();
+  const Fp<P> r2 = Fp<P>::r2();
   return fp_mul(fp_mul(r, r2), r2);
 }
+
+ZKP_HD_NOINLINE Fq fq_inv_gcd(const Fq& a) { return fp_inv_gcd_impl<FqParams>(a); }
+ZKP_HD_NOINLINE Fr fr_inv_gcd(const Fr& a) { return fp_inv_gcd_impl<FrParams>(a); }
 
 }  // namespace zkp

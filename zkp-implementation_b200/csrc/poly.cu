@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(PT) fr_batch_inverse_kernel(Fr* data, size_t n
     pre[i] = prod;
     prod = fp_mul(prod, ld_fr(data + start + i));
   }
-  Fr inv = fp_inv(prod);  // a zero entry zeroes its whole run (the reference panics on 1/0)
+  Fr inv = fr_inv_gcd(prod);  // division steps (inv_gcd.cuh); a zero entry zeroes its whole run (the reference panics on 1/0)
   for (uint32_t i = cnt; i-- > 0;) {
     const Fr v = ld_fr(data + start + i);
     st_fr(data + start + i, fp_mul(inv, pre[i]));
