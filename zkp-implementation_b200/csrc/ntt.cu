@@ -54,6 +54,12 @@ static constexpr uint32_t NTT_THREADS = NTT_THREADS_PER_CTA;
 #ifndef NTT_TW_PRELOAD
 #define NTT_TW_PRELOAD 1
 #endif
+#ifndef NTT_TW_PREFETCH2
+#define NTT_TW_PREFETCH2 0
+#endif
+#ifndef NTT_LOAD_BATCH
+#define NTT_LOAD_BATCH 4  // tile elements a thread requests before it stores the first one (1 = the plain loop)
+#endif
 
 struct NttPassArgs {
   const Fr* in;
@@ -148,6 +154,31 @@ __device__ __forceinline__ void tile_tw_load(TileTw<K>& tw, const TileGeom& g, u
   }
 }
 
+// Same addresses as tile_tw_load, requested into L1 without binding registers (the thread's SECOND work item of a step:
+// its twiddles would otherwise be fetched on demand after the first item's butterflies).
+template <int K>
+__device__ __forceinline__ void tile_tw_prefetch(const TileGeom& g, uint32_t l0, uint32_t it) {
+#ifndef ZKP_EMU
+  const uint32_t lo_bit = g.r - l0 - K;
+  const uint32_t c = it & ((1u << g.q) - 1);
+  const uint32_t dlow = (it >> g.q) & ((1u << lo_bit) - 1);
+  const uint32_t col = g.s_eff ? g.colbase + c : 0u;
+#pragma unroll
+  for (int t = 0; t < K; t++) {
+    const int hm = 1 << (K - 1 - t);
+    const uint32_t order_log = lo_bit + K - t;
+    const Fr* __restrict__ tk = g.w + ((size_t)1 << (order_log + g.s_eff - 1));
+#pragma unroll
+    for (int mm = 0; mm < hm; mm++) {
+      const uint32_t j = dlow + ((uint32_t)mm << lo_bit);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tk + (((size_t)j << g.s_eff) + col)));
+    }
+  }
+#else
+  (void)g; (void)l0; (void)it;
+#endif
+}
+
 template <int K>
 __device__ __forceinline__ void tile_block(uint4* lo, uint4* hi, const TileGeom& g, uint32_t l0, uint32_t it,
                                            const TileTw<K>& tw) {
@@ -192,6 +223,9 @@ __device__ __forceinline__ void tile_step(uint4* lo, uint4* hi, const TileGeom& 
   TileTw<K> tw;
 #if NTT_TW_PRELOAD
   if (tid < items) tile_tw_load<K>(tw, g, l0, tid);
+#if NTT_TW_PREFETCH2
+  if (tid + nthreads < items) tile_tw_prefetch<K>(g, l0, tid + nthreads);
+#endif
   __syncthreads();
   for (uint32_t it = tid; it < items; it += nthreads) {
     if (it != tid) tile_tw_load<K>(tw, g, l0, it);
@@ -234,6 +268,49 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
   }
 
   // ---- load (optionally scaled by the coset powers h^addr) ----
+  // Single-GPU passes: a thread's elements are requested NTT_LOAD_BATCH at a time before the first one is stored (the plain
+  // loop compiles to load -> wait -> store per element).  Measured on B200 (profiles/r02_ntt_variants.txt): 3.69 / 3.61 /
+  // 3.66 ms at 2^24 for batches of 1 / 4 / 8 -- the five resident CTAs already hide the load phase, so this is worth 1-2 %.
+  if constexpr (!DIST) {
+    // global address / tile slot of tile element idx
+    auto locate = [&](uint32_t idx, uint32_t& addr, uint32_t& sidx) {
+      if (a.mode == 0) {
+        const uint32_t c = idx & qmask, d = idx >> q;
+        addr = base + (d << s) + c;
+        sidx = idx;
+      } else {
+        const uint32_t d = idx & rmask, c = idx >> r;
+        const uint32_t k1 = (ab << q) + c;
+        addr = (((k1 << a.log_mid) + mid) << r) + d;
+        sidx = (d << q) + c;
+      }
+    };
+    for (uint32_t idx0 = tid; idx0 < E; idx0 += nthreads * NTT_LOAD_BATCH) {
+      Fr v[NTT_LOAD_BATCH];
+#pragma unroll
+      for (uint32_t u = 0; u < NTT_LOAD_BATCH; u++) {
+        const uint32_t idx = idx0 + u * nthreads;
+        if (idx < E) {
+          uint32_t addr, sidx;
+          locate(idx, addr, sidx);
+          v[u] = ld_fr(in + addr);
+        }
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < NTT_LOAD_BATCH; u++) {
+        const uint32_t idx = idx0 + u * nthreads;
+        if (idx < E) {
+          uint32_t addr, sidx;
+          locate(idx, addr, sidx);
+          if (a.pre_lo) {
+            v[u] = fp_mul(v[u], ldg_fr(a.pre_lo + (addr & ((1u << a.pre_lb) - 1))));
+            v[u] = fp_mul(v[u], ldg_fr(a.pre_hi + (addr >> a.pre_lb)));
+          }
+          st_tile(lo, hi, sidx, sw, v[u]);
+        }
+      }
+    }
+  } else {
   for (uint32_t idx = tid; idx < E; idx += nthreads) {
     uint32_t addr, sidx;
     const Fr* src = in;
@@ -278,6 +355,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a, const NttDis
     st_tile(lo, hi, sidx, sw, v);
   }
 
+  }  // DIST
   // ---- r DIF levels on the tile rows (result row d holds output digit bitrev_r(d)) ----
   TileGeom g;
   g.r = r; g.q = q; g.sw = sw;
