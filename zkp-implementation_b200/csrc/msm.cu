@@ -55,6 +55,9 @@ static constexpr uint32_t RED_THREADS = 128;
 #ifndef ZKP_RED_MIN_BLOCKS
 #define ZKP_RED_MIN_BLOCKS 1
 #endif
+#ifndef ZKP_ACC_MIN_BLOCKS
+#define ZKP_ACC_MIN_BLOCKS 1
+#endif
 static constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmTask {
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(256) msm_task_build_kernel(const uint32_t* __r
 // DIRECT = false: the run is a slice of the sorted (point index | sign) list and the points are gathered from `bases`;
 // DIRECT = true: the run is a slice of `bases` itself (the output of the batched-affine tree rounds, msm_affine.cu).
 template <bool DIRECT>
-__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks,
+__global__ void __launch_bounds__(ACC_THREADS, ZKP_ACC_MIN_BLOCKS) msm_accumulate_kernel(const MsmTask* __restrict__ tasks,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ ntasks_ptr,
                                                                      const uint32_t* __restrict__ svals,
