@@ -154,6 +154,33 @@ def test_msm_fixed_base_vs_oracle(zkp, gpu_engine, coracle, log_n):
     gpu_engine.srs_upload_dev(bases, 1)
 
 
+@pytest.mark.parametrize("window", [13, 15, 16, 17, 20])
+def test_msm_fixed_base_window_widths(zkp, gpu_engine, coracle, window):
+    """Fixed-base tables of several window widths at 2^17 points against the oracle: widths whose top window holds only a
+    few bits (15: the carry alone) pile every point into a handful of buckets (heavily split runs, the block-filled
+    start-bucket list of the affine rounds), 17 and 20 take three sort passes and a deeper reduction tree, and forced
+    affine rounds run on the short runs of the wide windows."""
+    import torch
+
+    F = zkp.fields
+    n = 1 << 17
+    bases = torch.zeros(n * 12, dtype=torch.int64, device="cuda")
+    gpu_engine.generate_bases_dev(0x9100, n, bases)
+    gpu_engine.srs_upload_dev(bases, n)
+    gpu_engine.srs_precompute(window)
+    s = F.random_fr_mont(0xA100 + window, n)
+    want = coracle.msm_pippenger(s, _host(bases, 12))
+    try:
+        for rounds in (-1, 2):
+            gpu_engine.set_msm_affine(rounds)
+            out, inf = gpu_engine.msm_dev(_dev(s), None, n)
+            assert gpu_engine.last_msm_shape()[0] == window
+            assert (out == want).all() and not inf, (window, rounds)
+    finally:
+        gpu_engine.set_msm_affine(-1)
+        gpu_engine.srs_upload_dev(bases, 1)
+
+
 def test_msm_2p24_fixed_base_properties(zkp, gpu_engine, pyref):
     """2^24 points through the fixed-base table (the bench's step): closed-form sum with equal scalars, and random
     scalars equal to the windowed path over the same points (two different bucket layouts, same group element)."""
