@@ -40,7 +40,8 @@ LOG_N_MSM = 24
 LOG_N_NTT = 24
 IMAD_PER_FQ_MUL = 300       # 12-limb CIOS = 2*12^2 + 12 multiply-adds
 FQ_MUL_PER_MADD = 10        # XYZZ mixed add 8M + 2S
-FQ_MUL_PER_AFFINE_ADD_KERNEL = 5   # batched-affine addition kernel: lambda, lambda^2, lambda*dx + 2 back-substitution products
+FQ_MUL_PER_AFFINE_ADD_KERNEL = 5 - 2 / 16  # batched-affine addition kernel: lambda, lambda^2, lambda*dx + 2 back-substitution
+                                          # products, the latter skipped for one of the K = 16 outputs of a thread
 IMAD_PER_FR_MUL = 136       # 8-limb CIOS = 2*8^2 + 8
 IMAD_PER_FR_MUL_SASS = 121  # what fp_mul<Fr> executes: 110 IMAD.WIDE + 11 IMAD (r = 1 mod 2^32 shortens the reduction rows)
 WORKLOAD = ("G1 MSM, 2^24 points per GPU (BLS12-381), random scalars < 2^254, resident SRS of distinct generated "

@@ -15,8 +15,8 @@
 //   C. additions     thread t walks its K outputs backwards: 1/den_k = inv * prefix_k, inv *= den_k, then
 //                    lambda = num / den, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1.
 // Prefixes and totals travel through HBM (about 0.5 KB per addition over a round, against ~1750 multiply-adds on
-// the integer pipe that bounds the kernel): products per addition = 6 + 1/K (the first prefix is 1) + 3/K (level B),
-// K = 16.
+// the integer pipe that bounds the kernel): products per addition = 6 - 2/K (element 0 of a thread: prefix 1, no running-inverse
+// update; -1/K more in A) + 3/K (level B), K = 16.
 // After R rounds every run is ~2^R times shorter; what is left goes through the XYZZ task kernel (msm.cu), which
 // also owns the splitting of heavily loaded buckets.
 //
@@ -206,8 +206,13 @@ __global__ void __launch_bounds__(AFF_THREADS, ZKP_AFF_A_BLOCKS) aff_denominator
       if (kind == AFF_DOUBLE) den = fp_dbl(p1.y);
       else if (kind != AFF_GENERAL) continue;
     }
-    st_fq(a.pre + o0 + k, run);
-    run = run * den;
+    // element 0 always sees run = 1: its prefix is never read (C uses inv itself) and the product by one is skipped
+    if (k == 0) {
+      run = den;
+    } else {
+      st_fq(a.pre + o0 + k, run);
+      run = run * den;
+    }
   }
   st_fq(a.tot + t, run);
 }
@@ -261,8 +266,12 @@ __global__ void __launch_bounds__(AFF_THREADS, ZKP_AFF_C_BLOCKS) aff_add_kernel(
         continue;
       }
     }
-    const Fq dinv = inv * ld_fq(a.pre + o0 + k);
-    inv = inv * den;
+    // the last element of the backward walk: its prefix is 1 and nobody needs the updated running inverse
+    Fq dinv = inv;
+    if (k > 0) {
+      dinv = inv * ld_fq(a.pre + o0 + k);
+      inv = inv * den;
+    }
     const Fq lam = num * dinv;
     G1Affine r;
     r.x = fp_sub(fp_sub(fp_sqr(lam), p1.x), p2.x);
