@@ -9,6 +9,7 @@
 //
 // The ranking is order-preserving (pairs with equal digits keep their input order), which is what makes the LSD
 // passes compose; it also makes the whole MSM pipeline run-to-run deterministic.
+#include <stdint.h>
 #include <string.h>
 
 #include "engine.h"
@@ -119,8 +120,20 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
   for (uint32_t d = tid; d < RS_DIGITS; d += RS_THREADS) cnt[d] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * RS_TILE;
-  for (uint32_t i = tid; i < RS_TILE; i += RS_THREADS)
-    if (base + i < n) atomicAdd(&cnt[rs_digit(keys[base + i], shift, mask, flip)], 1u);
+  const uint32_t count = (n - base < RS_TILE) ? (uint32_t)(n - base) : RS_TILE;
+  // four keys per 128-bit load when the tile is 16-byte aligned (the counts do not depend on the order): the scalar loop
+  // kept one 4-byte load per thread in flight
+  const uint32_t nvec = ((reinterpret_cast<uintptr_t>(keys + base) & 15u) == 0) ? (count >> 2) : 0u;
+  const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
+  for (uint32_t v = tid; v < nvec; v += RS_THREADS) {
+    const uint4 q = k4[v];
+    atomicAdd(&cnt[rs_digit(q.x, shift, mask, flip)], 1u);
+    atomicAdd(&cnt[rs_digit(q.y, shift, mask, flip)], 1u);
+    atomicAdd(&cnt[rs_digit(q.z, shift, mask, flip)], 1u);
+    atomicAdd(&cnt[rs_digit(q.w, shift, mask, flip)], 1u);
+  }
+  for (uint32_t i = (nvec << 2) + tid; i < count; i += RS_THREADS)
+    atomicAdd(&cnt[rs_digit(keys[base + i], shift, mask, flip)], 1u);
   __syncthreads();
   for (uint32_t d = tid; d <= mask; d += RS_THREADS) hist[(size_t)d * ntiles + blockIdx.x] = cnt[d];
 }
