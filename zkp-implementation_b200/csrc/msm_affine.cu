@@ -11,7 +11,8 @@
 //   A. denominators  thread t takes K consecutive outputs, multiplies their denominators into a running product,
 //                    stores the exclusive prefixes (48 B each) and its total;
 //   B. inversion     the per-thread totals are inverted by the same up-sweep / down-sweep, 16-fold per level, until
-//                    <= 4096 values are left for one Fermat inversion each (the only inversions of the round);
+//                    <= 4096 values are left for one inversion each (safegcd division steps, inv_gcd.cuh: the only
+//                    inversions of the round);
 //   C. additions     thread t walks its K outputs backwards: 1/den_k = inv * prefix_k, inv *= den_k, then
 //                    lambda = num / den, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1.
 // Prefixes and totals travel through HBM (about 0.5 KB per addition over a round, against ~1750 multiply-adds on
